@@ -1,0 +1,1023 @@
+// Fused per-map kernel: (normalise) -> threshold -> cut blend -> dominant-cluster filter
+// (HDBSCAN, bit-exact with oracle/hdbscan_port.py) -> 5x5 closing -> centroid / coverage.
+//
+// Replaces, per saliency map: unisal/train.py:1270-1274 (a1), sc_threshold
+// smartVidCrop.py:1050-1059 (a2), the raw-map sums of sc_compute_mean_sal :1304-1308 (a3), the
+// max profiles of sc_border_detection :859-865 (a4), sc_clustering_filt :1062-1161 and the cut
+// blend :2369-2373 (a6), sc_compute_cvrg_score :1310-1331 (a7), sc_find_center_of_mass
+// :1163-1219 with its emptiness gate :2403 (a8).
+//
+// One CTA owns one map at a time (persistent CTAs pull map indices from a device work list).
+// The map is staged in shared memory with one bulk-async (TMA) copy; after the salient pixels
+// are compacted the same shared memory is re-used for the clustering state, and the map is
+// rebuilt there for the closing.  Nothing but the input map, a 64-byte result record and (only
+// for maps a successor blends with, or on request) the filtered map touches HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvb {
+
+constexpr int kRingTableMax = 640;   // lattice offsets with d^2 <= kRingD2Max
+constexpr int kRingCountMax = 128;
+constexpr int kRingD2Max = 196;
+constexpr int kKeyShift = 13;        // Prim key = (weight << 13) | point index
+constexpr uint32_t kKeyIdxMask = (1u << kKeyShift) - 1;
+constexpr uint32_t kInTreeCore = 0x1FFFFu;  // larger than any squared distance on a 256x256 lattice
+constexpr int kLambdaBits = 46;      // oracle/hdbscan_port.py LAMBDA_FRAC_BITS
+constexpr uint16_t kNone16 = 0xFFFFu;
+
+struct RingTable {
+	int8_t dy[kRingTableMax];
+	int8_t dx[kRingTableMax];
+	uint16_t ring_end[kRingCountMax];
+	uint16_t ring_d2[kRingCountMax];
+	int n_rings;
+	int n_offsets;
+};
+
+// result record of one map
+struct MapOut {
+	double cx;            // centroid x (process px) or argmax x
+	double cy;
+	uint32_t raw_sum;     // sum of the raw uint8 map (mean saliency)
+	int32_t n_points;     // non-zero pixels after threshold/blend
+	int32_t n_clusters;   // -1: clustering skipped by the gates
+	int32_t kept_points;  // non-zero pixels of the final map
+	int32_t flags;        // bit0 empty, bit1 capacity overflow, bit2 core fallback used
+	int32_t pad;
+	double cvrg[8];       // coverage score per ratio
+};
+
+constexpr int kFlagEmpty = 1;
+constexpr int kFlagOverflow = 2;
+constexpr int kFlagCoreFallback = 4;
+constexpr int kFlagClusterCapacity = 8;
+
+// byte offsets into dynamic shared memory, computed on the host for (NMAX, H, WPS)
+struct SmemLayout {
+	int pts;       // u16[NMAX]   (y << 8) | x, row-major order
+	int val;       // u8[NMAX]
+	int u_base;    // start of the overlaid region
+	// phase 0/1/5 view of the overlaid region
+	int map;       // u8[H * WPS]
+	// clustering view
+	int a4;        // u32[NMAX]  core  -> later Lp1 (u16) + R (u16)
+	int order;     // u16[NMAX]
+	int wp;        // u32[NMAX]  edge weights in Prim order
+	int d4;        // u32[NMAX]  sort keys -> later cL (u16) + cR (u16)
+	int rank;      // u16[NMAX]  rank of edge -> later relabel
+	int pe;        // u16[NMAX]  parent edge of an edge node
+	int pl;        // u16[NMAX]  parent edge of a leaf
+	int queue;     // u16[NMAX]  BFS queue -> later cluster of a point
+	int pnode;     // u16[NMAX]  node a point fell out at (aliases d4: cL/cR are dead after the BFS)
+	int mask;      // u32[H * MW] occupancy bit mask (core distances); aliases d4.. (dead before the sort)
+	int cl_stab;   // u64[NCMAX]
+	int cl_birth;  // u64[NCMAX] lambda_fix at birth
+	int cl_acc;    // u32[NCMAX] per-label weight (sum or max)
+	int cl_parent; // u16[NCMAX]
+	int cl_ch0;    // u16[NCMAX]
+	int cl_ch1;    // u16[NCMAX]
+	int cl_label;  // u16[NCMAX] label of a selected cluster / kNone16
+	int cl_selanc; // u16[NCMAX] nearest selected ancestor-or-self
+	int total;
+	int nmax;
+	int ncmax;
+};
+
+struct MapArgs {
+	// input
+	const uint8_t *maps_u8;    // [N][H][gstride] or null
+	const float *maps_f32;     // [N][H][W] or null
+	int H, W, WPS, gstride;
+	// work list (persistent CTAs)
+	const int *list;
+	const int *list_len;
+	int *head;
+	int *ovf_list;             // maps that did not fit NMAX of this launch
+	int *ovf_len;
+	// per map
+	const int *pred;           // slot (in filt) of the predecessor whose filtered map is blended in, or -1
+	const int *store;          // slot (in filt) to write this map's filtered result to, or -1
+	const int *map_clip;       // clip index of a map
+	uint8_t *filt;             // [slots][H][fstride]
+	int fstride;
+	MapOut *out;
+	uint32_t *border_prof;     // [n_clips][H + W] max profiles, or null
+	const int *cvrg_cfg;       // [n_clips][R][2] = (mode, window) or null
+	int n_ratios;
+	int32_t *labels_dbg;       // optional: labels of the single map being debugged
+	// params
+	int t_threshold, clust_filt, mcs, min_samples, select_sum, op_close, com_km;
+	SmemLayout lay;
+};
+
+__constant__ RingTable c_rings;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32addr(const void *p) {
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t ok = 0;
+	while (!ok) {
+		asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+			"selp.u32 %0, 1, 0, p;\n"
+			"}\n" : "=r"(ok) : "r"(smem_u32addr(bar)), "r"(parity) : "memory");
+	}
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				 ::"r"(smem_u32addr(dst)), "l"(src), "r"(bytes), "r"(smem_u32addr(bar)) : "memory");
+}
+
+template <int NT>
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch /*[32]*/) {
+	v = __reduce_add_sync(0xffffffffu, v);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	__syncthreads();
+	if (lane == 0) scratch[warp] = v;
+	__syncthreads();
+	uint32_t t = (lane < NT / 32) ? scratch[lane] : 0u;
+	return __reduce_add_sync(0xffffffffu, t);
+}
+
+// exclusive scan of one value per thread across the block; returns (exclusive prefix, total)
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *scratch /*[32]*/, uint32_t &total) {
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += t;
+	}
+	__syncthreads();
+	if (lane == 31) scratch[warp] = inc;
+	__syncthreads();
+	uint32_t wsum = (lane < NT / 32) ? scratch[lane] : 0u;
+	uint32_t winc = wsum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+		if (lane >= o) winc += t;
+	}
+	total = __shfl_sync(0xffffffffu, winc, NT / 32 - 1);
+	uint32_t wexcl = __shfl_sync(0xffffffffu, winc - wsum, warp);
+	return wexcl + inc - v;
+}
+
+__device__ __forceinline__ uint64_t lambda_fix(uint32_t w) {
+	return (1ull << kLambdaBits) / (uint64_t)w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// numpy's portable argsort (aquicksort_<double>, npysort/quicksort.cpp) on packed keys
+// (weight << kKeyShift | edge).  Only the weight takes part in comparisons, exactly as
+// np.argsort(weights) would see them; must reproduce oracle/hdbscan_port.numpy_aquicksort.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool key_less(uint32_t a, uint32_t b) { return (a >> kKeyShift) < (b >> kKeyShift); }
+
+__device__ void np_aheapsort(uint32_t *t /* 0-based start of the range */, int n) {
+	uint32_t *a = t - 1;  // 1-based view like the C source
+	uint32_t tmp;
+	int i, j, l;
+	for (l = n >> 1; l > 0; --l) {
+		tmp = a[l];
+		for (i = l, j = l << 1; j <= n;) {
+			if (j < n && key_less(a[j], a[j + 1])) j += 1;
+			if (key_less(tmp, a[j])) {
+				a[i] = a[j];
+				i = j;
+				j += j;
+			} else {
+				break;
+			}
+		}
+		a[i] = tmp;
+	}
+	for (; n > 1;) {
+		tmp = a[n];
+		a[n] = a[1];
+		n -= 1;
+		for (i = 1, j = 2; j <= n;) {
+			if (j < n && key_less(a[j], a[j + 1])) j++;
+			if (key_less(tmp, a[j])) {
+				a[i] = a[j];
+				i = j;
+				j += j;
+			} else {
+				break;
+			}
+		}
+		a[i] = tmp;
+	}
+}
+
+__device__ void np_aquicksort(uint32_t *t, int num) {
+	if (num < 2) return;
+	constexpr int kSmall = 15;  // partitions of >= 17 elements are split (numpy 2.x, verified against np.argsort)
+	int stack_l[64], stack_r[64], stack_d[64];
+	int sp = 0;
+	int pl = 0, pr = num - 1;
+	int cdepth = (31 - __clz(num)) * 2;
+	while (true) {
+		bool heap = false;
+		if (cdepth < 0) {
+			np_aheapsort(t + pl, pr - pl + 1);
+			heap = true;
+		}
+		if (!heap) {
+			while ((pr - pl) > kSmall) {
+				int pm = pl + ((pr - pl) >> 1);
+				uint32_t vl = t[pl], vm = t[pm], vr = t[pr];
+				if (key_less(vm, vl)) { uint32_t s = vm; vm = vl; vl = s; }
+				if (key_less(vr, vm)) { uint32_t s = vr; vr = vm; vm = s; }
+				if (key_less(vm, vl)) { uint32_t s = vm; vm = vl; vl = s; }
+				t[pl] = vl;
+				t[pr] = vr;
+				const uint32_t vp = vm;
+				int pi = pl;
+				int pj = pr - 1;
+				// INTP_SWAP(*pm, *pj)
+				t[pm] = t[pj];
+				t[pj] = vp;
+				for (;;) {
+					uint32_t vi, vj;
+					do { ++pi; vi = t[pi]; } while (key_less(vi, vp));
+					do { --pj; vj = t[pj]; } while (key_less(vp, vj));
+					if (pi >= pj) break;
+					t[pi] = vj;
+					t[pj] = vi;
+				}
+				int pk = pr - 1;
+				uint32_t s = t[pi];
+				t[pi] = t[pk];
+				t[pk] = s;
+				if (pi - pl < pr - pi) {
+					stack_l[sp] = pi + 1;
+					stack_r[sp] = pr;
+					pr = pi - 1;
+				} else {
+					stack_l[sp] = pl;
+					stack_r[sp] = pi - 1;
+					pl = pi + 1;
+				}
+				stack_d[sp] = --cdepth;
+				++sp;
+			}
+			for (int pi = pl + 1; pi <= pr; ++pi) {
+				uint32_t vi = t[pi];
+				int pj = pi;
+				while (pj > pl) {
+					uint32_t vk = t[pj - 1];
+					if (!key_less(vi, vk)) break;
+					t[pj] = vk;
+					--pj;
+				}
+				t[pj] = vi;
+			}
+		}
+		if (sp == 0) break;
+		--sp;
+		pl = stack_l[sp];
+		pr = stack_r[sp];
+		cdepth = stack_d[sp];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// separable 5x5 max / min on a byte image held in shared memory (words of 4 pixels).
+// OpenCV's default morphology border never wins, i.e. windows are clipped to the image.
+// ---------------------------------------------------------------------------------------------
+template <int NT, bool IS_MAX>
+__device__ __forceinline__ void morph_pass_h(uint32_t *img, int H, int MWS) {
+	// 1x5 along x, in place: one warp owns a row, loads everything it needs, then stores
+	const uint32_t neutral = IS_MAX ? 0u : 0xFFFFFFFFu;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int y = warp; y < H; y += NT / 32) {
+		uint32_t *row = img + y * MWS;
+		uint32_t res[2];
+#pragma unroll
+		for (int k = 0; k < 2; ++k) {
+			const int xw = lane + 32 * k;
+			uint32_t r = 0;
+			if (xw < MWS) {
+				const uint32_t C = row[xw];
+				const uint32_t P = (xw > 0) ? row[xw - 1] : neutral;
+				const uint32_t N = (xw + 1 < MWS) ? row[xw + 1] : neutral;
+				const uint32_t m2 = __funnelshift_l(P, C, 16);  // pixels x-2
+				const uint32_t m1 = __funnelshift_l(P, C, 8);   // pixels x-1
+				const uint32_t p1 = __funnelshift_r(C, N, 8);   // pixels x+1
+				const uint32_t p2 = __funnelshift_r(C, N, 16);  // pixels x+2
+				if (IS_MAX) r = __vmaxu4(__vmaxu4(__vmaxu4(m2, m1), __vmaxu4(p1, p2)), C);
+				else r = __vminu4(__vminu4(__vminu4(m2, m1), __vminu4(p1, p2)), C);
+			}
+			res[k] = r;
+		}
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < 2; ++k) {
+			const int xw = lane + 32 * k;
+			if (xw < MWS) row[xw] = res[k];
+		}
+	}
+	__syncthreads();
+}
+
+template <int NT, bool IS_MAX>
+__device__ __forceinline__ void morph_pass_v(uint32_t *img, int H, int MWS) {
+	// 5x1 along y, in place: a thread owns a vertical segment of one word column; the two rows above
+	// and below the segment are read before anybody writes, then a sliding window runs down it
+	const uint32_t neutral = IS_MAX ? 0u : 0xFFFFFFFFu;
+	const int nseg = max(1, NT / MWS);
+	const int seg_rows = (H + nseg - 1) / nseg;
+	const int xw = threadIdx.x % MWS, seg = threadIdx.x / MWS;
+	const int y0 = seg * seg_rows, y1 = min(H, y0 + seg_rows);
+	const bool active = (seg < nseg) && (y0 < H);
+	auto at = [&](int y) -> uint32_t { return (y >= 0 && y < H) ? img[y * MWS + xw] : neutral; };
+	uint32_t a2 = neutral, a1 = neutral, b1 = neutral, b2 = neutral;
+	if (active) { a2 = at(y0 - 2); a1 = at(y0 - 1); b1 = at(y1); b2 = at(y1 + 1); }
+	__syncthreads();
+	if (active) {
+		// window registers: m2, m1 (originals of the two previous rows), c, p1, p2
+		uint32_t m2 = a2, m1 = a1;
+		uint32_t c = img[y0 * MWS + xw];
+		uint32_t p1 = (y0 + 1 < y1) ? img[(y0 + 1) * MWS + xw] : ((y0 + 1 == y1) ? b1 : b2);
+		for (int y = y0; y < y1; ++y) {
+			uint32_t p2;
+			const int yy = y + 2;
+			if (yy < y1) p2 = img[yy * MWS + xw];
+			else if (yy == y1) p2 = b1;
+			else if (yy == y1 + 1) p2 = b2;
+			else p2 = neutral;
+			uint32_t r;
+			if (IS_MAX) r = __vmaxu4(__vmaxu4(__vmaxu4(m2, m1), __vmaxu4(p1, p2)), c);
+			else r = __vminu4(__vminu4(__vminu4(m2, m1), __vminu4(p1, p2)), c);
+			img[y * MWS + xw] = r;
+			m2 = m1; m1 = c; c = p1; p1 = p2;
+		}
+	}
+	__syncthreads();
+}
+
+// set the padding bytes (x >= W) of every row to `fill`
+__device__ __forceinline__ void set_row_padding(uint32_t *img, int H, int W, int MWS, uint32_t fill_byte, int NT) {
+	const int first_pad_word = W >> 2;
+	const int pad_words = MWS - first_pad_word;
+	for (int i = threadIdx.x; i < H * pad_words; i += NT) {
+		const int y = i / pad_words, k = i - y * pad_words;
+		const int xw = first_pad_word + k;
+		uint32_t keep_mask = 0u;
+		if (xw == first_pad_word) {
+			const int valid = W & 3;
+			keep_mask = valid ? ((1u << (8 * valid)) - 1u) : 0u;
+		}
+		const uint32_t fill = fill_byte * 0x01010101u;
+		uint32_t v = img[y * MWS + xw];
+		img[y * MWS + xw] = (v & keep_mask) | (fill & ~keep_mask);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+struct MapScalars {
+	unsigned long long mbar;
+	uint32_t red[32];
+	uint32_t wmin[2][32];
+	int map_idx;
+	int n;
+	int ncl;
+	int nsel;
+	int maxcl;
+	int n_clusters;
+	int fb_count;
+	int err;
+	uint32_t rootminw;
+	uint32_t root_edge;
+	unsigned long long sx, sy;
+	uint32_t cnt, tot;
+	uint32_t argmax_key;
+};
+
+template <int NT, int TPT>
+__global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ MapScalars S;
+	const SmemLayout &L = a.lay;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int NW = NT / 32;
+	const int H = a.H, W = a.W, WPS = a.WPS, MWS = WPS >> 2;
+	const int n_words = H * MWS;
+
+	uint16_t *pts = reinterpret_cast<uint16_t *>(smem + L.pts);
+	uint8_t *val = smem + L.val;
+	uint8_t *map8 = smem + L.map;
+	uint32_t *map32 = reinterpret_cast<uint32_t *>(smem + L.map);
+
+	if (tid == 0) {
+		mbar_init(reinterpret_cast<uint64_t *>(&S.mbar), 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	uint32_t tma_parity = 0;
+
+	while (true) {
+		// ---- fetch the next map ---------------------------------------------------------------
+		__syncthreads();
+		if (tid == 0) {
+			const int i = atomicAdd(a.head, 1);
+			S.map_idx = (i < *a.list_len) ? a.list[i] : -1;
+		}
+		__syncthreads();
+		const int m = S.map_idx;
+		if (m < 0) break;
+		MapOut res;
+		res.cx = 0.0; res.cy = 0.0; res.raw_sum = 0; res.n_points = 0; res.n_clusters = -1;
+		res.kept_points = 0; res.flags = 0; res.pad = 0;
+#pragma unroll
+		for (int r = 0; r < 8; ++r) res.cvrg[r] = 0.0;
+
+		// ---- phase 0: stage the map in shared memory --------------------------------------------
+		if (a.maps_u8 != nullptr) {
+			const uint8_t *src = a.maps_u8 + (size_t)m * H * a.gstride;
+			if (a.gstride == WPS) {
+				if (tid == 0) {
+					// earlier generic-proxy accesses to this shared memory must be ordered before the
+					// async-proxy write of the bulk copy
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					mbar_expect_tx(reinterpret_cast<uint64_t *>(&S.mbar), (uint32_t)(H * WPS));
+					tma_bulk_g2s(map8, src, (uint32_t)(H * WPS), reinterpret_cast<uint64_t *>(&S.mbar));
+				}
+				mbar_wait(reinterpret_cast<uint64_t *>(&S.mbar), tma_parity);
+				tma_parity ^= 1u;
+			} else {
+				for (int i = tid; i < n_words; i += NT) {
+					const int y = i / MWS, xw = i - y * MWS;
+					uint32_t v = 0;
+					if (xw * 4 < a.gstride) v = *reinterpret_cast<const uint32_t *>(src + (size_t)y * a.gstride + xw * 4);
+					map32[i] = v;
+				}
+			}
+		} else {
+			// a1: u8 = trunc( exp(logp) / max(exp(logp)) * 255 ), fp32 arithmetic, exp correctly rounded
+			const float *src = a.maps_f32 + (size_t)m * H * W;
+			const int n_px = H * W;
+			float mx = -INFINITY;
+			for (int i = tid * 4; i < n_px; i += NT * 4) {
+				if (i + 3 < n_px) {
+					const float4 v = *reinterpret_cast<const float4 *>(src + i);
+					mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+				} else {
+					for (int k = i; k < n_px; ++k) mx = fmaxf(mx, src[k]);
+				}
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+			__syncthreads();
+			if (lane == 0) S.red[warp] = __float_as_uint(mx);
+			__syncthreads();
+			mx = __uint_as_float(S.red[0]);
+			for (int wv = 1; wv < NW; ++wv) mx = fmaxf(mx, __uint_as_float(S.red[wv]));
+			const float emax = (float)exp((double)mx);
+			for (int i = tid; i < n_words; i += NT) map32[i] = 0u;
+			__syncthreads();
+			for (int i = tid; i < n_px; i += NT) {
+				const float e = (float)exp((double)src[i]);
+				const float q = __fmul_rn(__fdiv_rn(e, emax), 255.0f);
+				const int y = i / W, x = i - y * W;
+				map8[y * WPS + x] = (uint8_t)(int)q;
+			}
+		}
+		__syncthreads();
+
+		// raw statistics, threshold, blend -- one pass over the words
+		{
+			const int pred = a.pred ? a.pred[m] : -1;
+			const uint8_t *pf = (pred >= 0) ? (a.filt + (size_t)pred * H * a.fstride) : nullptr;
+			const uint32_t thr4 = (uint32_t)a.t_threshold * 0x01010101u;
+			const int first_pad_word = W >> 2;
+			uint32_t raw = 0;
+			for (int i = tid; i < n_words; i += NT) {
+				const int y = i / MWS, xw = i - y * MWS;
+				uint32_t v = map32[i];
+				if (xw >= first_pad_word) {
+					const int valid = (xw == first_pad_word) ? (W & 3) : 0;
+					v &= valid ? ((1u << (8 * valid)) - 1u) : 0u;
+				}
+				raw += __vsadu4(v, 0u);
+				if (a.t_threshold > 255) v = 0u;
+				else v &= __vcmpgeu4(v, thr4);
+				if (pf != nullptr) {
+					uint32_t f = 0u;
+					if (xw * 4 < a.fstride) f = *reinterpret_cast<const uint32_t *>(pf + (size_t)y * a.fstride + xw * 4);
+					if (xw >= first_pad_word) {
+						const int valid = (xw == first_pad_word) ? (W & 3) : 0;
+						f &= valid ? ((1u << (8 * valid)) - 1u) : 0u;
+					}
+					// uint8 addition wraps, then /2 truncates (smartVidCrop.py:2371-2373)
+					v = (__vadd4(v, f) >> 1) & 0x7F7F7F7Fu;
+				}
+				map32[i] = v;
+			}
+			// border max profiles of the RAW map are taken before the threshold; they need a second
+			// look at the raw values, so they are handled by border_profile_kernel on request.
+			res.raw_sum = block_sum_u32<NT>(raw, S.red);
+		}
+		__syncthreads();
+
+		// ---- phase 1: compact the non-zero pixels in row-major order ----------------------------
+		int n;
+		{
+			const int chunk = (n_words + NT - 1) / NT;
+			const int w0 = tid * chunk, w1 = min(n_words, w0 + chunk);
+			uint32_t c = 0;
+			for (int i = w0; i < w1; ++i) c += __popc(__vcmpne4(map32[i], 0u)) >> 3;
+			uint32_t total;
+			uint32_t base = block_excl_scan<NT>(c, S.red, total);
+			n = (int)total;
+			if (n <= L.nmax) {
+				for (int i = w0; i < w1; ++i) {
+					uint32_t v = map32[i];
+					if (v == 0u) continue;
+					const int y = i / MWS, x0 = (i - y * MWS) * 4;
+#pragma unroll
+					for (int b = 0; b < 4; ++b) {
+						const uint32_t bv = (v >> (8 * b)) & 0xFFu;
+						if (bv) {
+							pts[base] = (uint16_t)((y << 8) | (x0 + b));
+							val[base] = (uint8_t)bv;
+							++base;
+						}
+					}
+				}
+			}
+		}
+		res.n_points = n;
+		__syncthreads();
+		if (n > L.nmax) {
+			// does not fit this launch's capacity: hand it to the next size class
+			if (tid == 0) {
+				if (a.ovf_list != nullptr) {
+					const int k = atomicAdd(a.ovf_len, 1);
+					a.ovf_list[k] = m;
+				} else {
+					res.flags = kFlagOverflow;
+					a.out[m] = res;
+				}
+			}
+			continue;
+		}
+
+		const bool do_cluster = a.clust_filt && n > 0 && (n > a.mcs + 1);
+		bool rebuilt = false;
+		if (do_cluster) {
+			uint32_t *core = reinterpret_cast<uint32_t *>(smem + L.a4);
+			uint16_t *Lp1 = reinterpret_cast<uint16_t *>(smem + L.a4);
+			uint16_t *Rr = Lp1 + L.nmax;
+			uint16_t *order = reinterpret_cast<uint16_t *>(smem + L.order);
+			uint32_t *wp = reinterpret_cast<uint32_t *>(smem + L.wp);
+			uint32_t *skey = reinterpret_cast<uint32_t *>(smem + L.d4);
+			uint16_t *cL = reinterpret_cast<uint16_t *>(smem + L.d4);
+			uint16_t *cR = cL + L.nmax;
+			uint16_t *rank = reinterpret_cast<uint16_t *>(smem + L.rank);
+			uint16_t *relabel = rank;
+			uint16_t *pe = reinterpret_cast<uint16_t *>(smem + L.pe);
+			uint16_t *pl = reinterpret_cast<uint16_t *>(smem + L.pl);
+			uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.queue);
+			uint16_t *pcl = queue;
+			uint16_t *pnode = reinterpret_cast<uint16_t *>(smem + L.pnode);
+			uint32_t *mask = reinterpret_cast<uint32_t *>(smem + L.mask);
+			unsigned long long *cl_stab = reinterpret_cast<unsigned long long *>(smem + L.cl_stab);
+			unsigned long long *cl_birth = reinterpret_cast<unsigned long long *>(smem + L.cl_birth);
+			uint32_t *cl_acc = reinterpret_cast<uint32_t *>(smem + L.cl_acc);
+			uint16_t *cl_parent = reinterpret_cast<uint16_t *>(smem + L.cl_parent);
+			uint16_t *cl_ch0 = reinterpret_cast<uint16_t *>(smem + L.cl_ch0);
+			uint16_t *cl_ch1 = reinterpret_cast<uint16_t *>(smem + L.cl_ch1);
+			uint16_t *cl_label = reinterpret_cast<uint16_t *>(smem + L.cl_label);
+			uint16_t *cl_selanc = reinterpret_cast<uint16_t *>(smem + L.cl_selanc);
+			const int MW = (W + 31) >> 5;
+
+			// ---- phase 2: core distances on the lattice -------------------------------------------
+			// k-th nearest OTHER salient pixel (hdbscan: sorted-row index min_samples, self at 0).
+			int kk = (a.min_samples > 0) ? a.min_samples : a.mcs;
+			kk = min(n - 1, kk);
+			if (kk == 0) kk = 1;
+			for (int i = tid; i < H * MW; i += NT) mask[i] = 0u;
+			if (tid == 0) S.fb_count = 0;
+			__syncthreads();
+			for (int p = tid; p < n; p += NT) {
+				const int y = pts[p] >> 8, x = pts[p] & 0xFF;
+				atomicOr(&mask[y * MW + (x >> 5)], 1u << (x & 31));
+			}
+			__syncthreads();
+			for (int p0 = 0; p0 < n; p0 += NT) {
+				const int p = p0 + tid;
+				bool active = p < n;
+				const int y = active ? (pts[p] >> 8) : 0, x = active ? (pts[p] & 0xFF) : 0;
+				int cnt = 0, i = 0;
+				uint32_t cd = 0;
+				for (int r = 0; r < c_rings.n_rings; ++r) {
+					const int e = c_rings.ring_end[r];
+					if (active) {
+						for (; i < e; ++i) {
+							const int yy = y + c_rings.dy[i], xx = x + c_rings.dx[i];
+							if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W)
+								cnt += (mask[yy * MW + (xx >> 5)] >> (xx & 31)) & 1u;
+						}
+						if (cnt >= kk) {
+							cd = c_rings.ring_d2[r];
+							active = false;
+						}
+					}
+					if (!__any_sync(0xffffffffu, active)) break;
+				}
+				if (p < n) {
+					core[p] = cd;
+					if (cd == 0) {  // not resolved inside the table radius
+						const int k = atomicAdd(&S.fb_count, 1);
+						queue[k] = (uint16_t)p;
+					}
+				}
+			}
+			__syncthreads();
+			if (S.fb_count > 0) {
+				// rare: sparse pixels.  One warp per pixel, bisection on the squared radius.
+				res.flags |= kFlagCoreFallback;
+				const int fbn = S.fb_count;
+				for (int f = warp; f < fbn; f += NW) {
+					const int p = queue[f];
+					const int y = pts[p] >> 8, x = pts[p] & 0xFF;
+					int lo = kRingD2Max + 1, hi = H * H + W * W;
+					while (lo < hi) {
+						const int mid = (lo + hi) >> 1;
+						int c = 0;
+						for (int j = lane; j < n; j += 32) {
+							const int dy = (pts[j] >> 8) - y, dx = (pts[j] & 0xFF) - x;
+							c += (dy * dy + dx * dx <= mid) ? 1 : 0;
+						}
+						c = __reduce_add_sync(0xffffffffu, c) - 1;  // minus self
+						if (c >= kk) hi = mid; else lo = mid + 1;
+					}
+					if (lane == 0) core[p] = (uint32_t)lo;
+				}
+				__syncthreads();
+			}
+
+			// ---- phase 3: Prim on the mutual-reachability graph -------------------------------------
+			// from point 0, lowest index wins ties (np.argmin), _linkage.pyx:97-112.  Each thread keeps
+			// its TPT points in registers; key = (min reachability << 13) | index.
+			{
+				int px[TPT], py[TPT];
+				uint32_t pc[TPT], key[TPT];
+#pragma unroll
+				for (int i = 0; i < TPT; ++i) {
+					const int j = tid + i * NT;
+					if (j < n) {
+						px[i] = pts[j] & 0xFF;
+						py[i] = pts[j] >> 8;
+						pc[i] = core[j];
+					} else {
+						px[i] = 0; py[i] = 0;
+						pc[i] = kInTreeCore;
+					}
+					key[i] = 0xFFFFFFFFu;
+				}
+				if (tid == 0) {
+					pc[0] = kInTreeCore;  // point 0 starts the tree
+					order[0] = 0;
+				}
+				int cx = pts[0] & 0xFF, cy = pts[0] >> 8;
+				uint32_t cc = core[0];
+				for (int step = 0; step < n - 1; ++step) {
+					uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+					for (int i = 0; i < TPT; ++i) {
+						const int dx = px[i] - cx, dy = py[i] - cy;
+						uint32_t mr = (uint32_t)(dx * dx + dy * dy);
+						mr = max(mr, max(pc[i], cc));
+						const uint32_t k = (mr << kKeyShift) | (uint32_t)(tid + i * NT);
+						key[i] = min(key[i], k);
+						best = min(best, key[i]);
+					}
+					best = __reduce_min_sync(0xffffffffu, best);
+					uint32_t *wm = S.wmin[step & 1];
+					if (lane == 0) wm[warp] = best;
+					__syncthreads();
+					uint32_t g = (lane < NW) ? wm[lane] : 0xFFFFFFFFu;
+					g = __reduce_min_sync(0xffffffffu, g);
+					const int nj = (int)(g & kKeyIdxMask);
+					if (tid == 0) {
+						order[step + 1] = (uint16_t)nj;
+						wp[step] = g >> kKeyShift;
+					}
+					// the owner retires the new node
+					if ((nj % NT) == tid) {
+						const int slot = nj / NT;
+#pragma unroll
+						for (int i = 0; i < TPT; ++i)
+							if (i == slot) { pc[i] = kInTreeCore; key[i] = 0xFFFFFFFFu; }
+					}
+					cx = pts[nj] & 0xFF;
+					cy = pts[nj] >> 8;
+					cc = core[nj];
+				}
+			}
+			__syncthreads();
+
+			// ---- phase 4a: numpy's unstable argsort of the edge weights ------------------------------
+			const int ne = n - 1;
+			for (int e = tid; e < ne; e += NT) skey[e] = (wp[e] << kKeyShift) | (uint32_t)e;
+			__syncthreads();
+			if (tid == 0) np_aquicksort(skey, ne);
+			__syncthreads();
+			for (int r = tid; r < ne; r += NT) rank[skey[r] & kKeyIdxMask] = (uint16_t)r;
+			if (tid == 0) S.root_edge = skey[ne - 1] & kKeyIdxMask;
+			__syncthreads();
+
+			// ---- phase 4b: the dendrogram as a Cartesian tree over Prim positions --------------------
+			// Edge e joins positions e and e+1 at time rank[e]; at that time its cluster is the maximal
+			// interval around e whose edges all have smaller rank (make_single_linkage, _linkage.pyx:226).
+			for (int e = tid; e < ne; e += NT) {
+				const uint32_t re = rank[e];
+				int l = e - 1;
+				while (l >= 0 && rank[l] < re) --l;
+				int r = e + 1;
+				while (r < ne && rank[r] < re) ++r;
+				Lp1[e] = (uint16_t)(l + 1);
+				Rr[e] = (uint16_t)r;  // points L+1 .. R  (R == ne means "to the last point")
+				uint16_t par;
+				if (l < 0 && r >= ne) par = kNone16;
+				else if (l < 0) par = (uint16_t)r;
+				else if (r >= ne) par = (uint16_t)l;
+				else par = (rank[l] < rank[r]) ? (uint16_t)l : (uint16_t)r;
+				pe[e] = par;
+			}
+			__syncthreads();
+			// skey is dead from here: its storage becomes cL / cR
+			for (int e = tid; e < ne; e += NT) { cL[e] = kNone16; cR[e] = kNone16; }
+			__syncthreads();
+			for (int e = tid; e < ne; e += NT) {
+				const uint16_t p = pe[e];
+				if (p != kNone16) {
+					if (e < (int)p) cL[p] = (uint16_t)e; else cR[p] = (uint16_t)e;
+				}
+			}
+			for (int q = tid; q < n; q += NT) {
+				uint16_t par;
+				if (q == 0) par = 0;
+				else if (q == n - 1) par = (uint16_t)(ne - 1);
+				else par = (rank[q - 1] < rank[q]) ? (uint16_t)(q - 1) : (uint16_t)q;
+				pl[q] = par;
+			}
+			__syncthreads();
+
+			// ---- phase 4c: condensed tree over the big nodes, breadth first (_condense_tree) ---------
+			// rank[] is dead from here: its storage becomes relabel[]
+			const int mcs = a.mcs;
+			if (tid == 0) {
+				S.err = 0;
+				S.rootminw = 0xFFFFFFFFu;
+				int ncl = 1;
+				cl_stab[0] = 0ull; cl_birth[0] = 0ull; cl_parent[0] = kNone16; cl_ch0[0] = kNone16; cl_ch1[0] = kNone16;
+				int qh = 0, qt = 0;
+				const int root = (int)S.root_edge;
+				relabel[root] = 0;
+				queue[qt++] = (uint16_t)root;
+				uint32_t rootminw = 0xFFFFFFFFu;
+				while (qh < qt) {
+					const int e = queue[qh++];
+					const int c = relabel[e];
+					const int lc = e + 1 - (int)Lp1[e];
+					const int rc = (int)Rr[e] - e;
+					if (lc >= mcs && rc >= mcs) {
+						if (ncl + 2 > L.ncmax) { S.err = 1; break; }
+						const uint32_t w = wp[e];
+						const unsigned long long lam = lambda_fix(w);
+						const int ca = ncl++, cb = ncl++;
+						cl_stab[ca] = 0ull; cl_stab[cb] = 0ull;
+						cl_birth[ca] = lam; cl_birth[cb] = lam;
+						cl_parent[ca] = (uint16_t)c; cl_parent[cb] = (uint16_t)c;
+						cl_ch0[ca] = kNone16; cl_ch1[ca] = kNone16; cl_ch0[cb] = kNone16; cl_ch1[cb] = kNone16;
+						cl_ch0[c] = (uint16_t)ca; cl_ch1[c] = (uint16_t)cb;
+						cl_stab[c] += (lam - cl_birth[c]) * (unsigned long long)(lc + rc);
+						if (c == 0) rootminw = min(rootminw, w);
+						relabel[cL[e]] = (uint16_t)ca;
+						relabel[cR[e]] = (uint16_t)cb;
+						queue[qt++] = cL[e];
+						queue[qt++] = cR[e];
+					} else if (lc >= mcs) {
+						relabel[cL[e]] = (uint16_t)c;
+						queue[qt++] = cL[e];
+					} else if (rc >= mcs) {
+						relabel[cR[e]] = (uint16_t)c;
+						queue[qt++] = cR[e];
+					}
+				}
+				S.ncl = ncl;
+				S.rootminw = rootminw;
+			}
+			__syncthreads();
+			if (S.err) {
+				if (tid == 0) { res.flags |= kFlagClusterCapacity; a.out[m] = res; }
+				continue;
+			}
+
+			// ---- phase 4d: where each point falls out (the queue storage becomes pcl[]) --------------
+			for (int q = tid; q < n; q += NT) {
+				int node = pl[q];
+				while (((int)Rr[node] + 1 - (int)Lp1[node]) < mcs) node = pe[node];
+				const int c = relabel[node];
+				const uint32_t w = wp[node];
+				pcl[q] = (uint16_t)c;
+				pnode[q] = (uint16_t)node;
+				atomicAdd(&cl_stab[c], lambda_fix(w) - cl_birth[c]);
+				if (c == 0) atomicMin(&S.rootminw, w);
+			}
+			__syncthreads();
+
+			// ---- phase 4e: excess of mass, allow_single_cluster=True (_get_clusters) -----------------
+			if (tid == 0) {
+				const int ncl = S.ncl;
+				// bottom-up (children have larger ids): does the node beat its subtree?
+				for (int c = ncl - 1; c >= 0; --c) {
+					bool win = true;
+					if (cl_ch0[c] != kNone16) {
+						const unsigned long long sub = cl_stab[cl_ch0[c]] + cl_stab[cl_ch1[c]];
+						if (sub > cl_stab[c]) { win = false; cl_stab[c] = sub; }
+					}
+					cl_label[c] = win ? 1 : 0;
+				}
+				// top-down: a winner with a winning ancestor is dropped; number the survivors by id
+				int nsel = 0;
+				for (int c = 0; c < ncl; ++c) {
+					const uint16_t par = cl_parent[c];
+					const uint16_t anc = (par == kNone16) ? kNone16 : cl_selanc[par];
+					if (anc != kNone16) { cl_selanc[c] = anc; cl_label[c] = kNone16; }
+					else if (cl_label[c]) { cl_selanc[c] = (uint16_t)c; cl_label[c] = (uint16_t)nsel++; }
+					else { cl_selanc[c] = kNone16; cl_label[c] = kNone16; }
+				}
+				S.nsel = nsel;
+				for (int i = 0; i < nsel; ++i) cl_acc[i] = 0u;
+			}
+			__syncthreads();
+
+			// ---- phase 4f: labels (_do_labelling) and the dominant cluster (smartVidCrop.py:1107-1121) -
+			const uint32_t rootminw = S.rootminw;
+			for (int q = tid; q < n; q += NT) {
+				const uint16_t s = cl_selanc[pcl[q]];
+				uint16_t lab = kNone16;
+				if (s != kNone16) {
+					if (s != 0) lab = cl_label[s];
+					else if (wp[pnode[q]] <= rootminw) lab = cl_label[0];
+				}
+				pcl[q] = lab;
+				if (lab != kNone16) {
+					const uint32_t v = val[order[q]];
+					if (a.select_sum == 1) atomicAdd(&cl_acc[lab], v); else atomicMax(&cl_acc[lab], v);
+				}
+			}
+			__syncthreads();
+			if (tid == 0) {
+				// every selected cluster owns at least one labelled point, so n_clusters == nsel
+				int best = 0;
+				for (int i = 1; i < S.nsel; ++i) if (cl_acc[i] > cl_acc[best]) best = i;
+				S.maxcl = best;
+				S.n_clusters = S.nsel;
+			}
+			__syncthreads();
+			res.n_clusters = S.n_clusters;
+			if (a.labels_dbg != nullptr)
+				for (int q = tid; q < n; q += NT) a.labels_dbg[order[q]] = (pcl[q] == kNone16) ? -1 : (int)pcl[q];
+			if (S.n_clusters > 0) {
+				const uint16_t keep = (uint16_t)S.maxcl;
+				for (int q = tid; q < n; q += NT) if (pcl[q] != keep) val[order[q]] = 0;
+			}
+			__syncthreads();
+
+			// ---- phase 5: rebuild the map, close it --------------------------------------------------
+			for (int i = tid; i < n_words; i += NT) map32[i] = 0u;
+			__syncthreads();
+			for (int p = tid; p < n; p += NT) map8[(pts[p] >> 8) * WPS + (pts[p] & 0xFF)] = val[p];
+			__syncthreads();
+			rebuilt = true;
+			if (a.op_close && S.n_clusters > 0) {
+				morph_pass_h<NT, true>(map32, H, MWS);
+				morph_pass_v<NT, true>(map32, H, MWS);
+				set_row_padding(map32, H, W, MWS, 0xFFu, NT);
+				__syncthreads();
+				morph_pass_h<NT, false>(map32, H, MWS);
+				morph_pass_v<NT, false>(map32, H, MWS);
+				set_row_padding(map32, H, W, MWS, 0x00u, NT);
+				__syncthreads();
+			}
+		}
+		(void)rebuilt;
+
+		// ---- phase 6: results -------------------------------------------------------------------------
+		if (tid == 0) { S.sx = 0ull; S.sy = 0ull; S.cnt = 0u; S.tot = 0u; S.argmax_key = 0u; }
+		__syncthreads();
+		{
+			uint32_t cnt = 0, tot = 0, sx = 0, sy = 0, amax = 0;
+			for (int i = tid; i < n_words; i += NT) {
+				const uint32_t v = map32[i];
+				if (v == 0u) continue;
+				const int y = i / MWS, x0 = (i - y * MWS) * 4;
+				tot += __vsadu4(v, 0u);
+#pragma unroll
+				for (int b = 0; b < 4; ++b) {
+					const uint32_t bv = (v >> (8 * b)) & 0xFFu;
+					if (bv) {
+						++cnt; sx += x0 + b; sy += y;
+						// first maximum in row-major order: larger value, then smaller linear index
+						const uint32_t lin = (uint32_t)(y * W + x0 + b);
+						const uint32_t k = (bv << 20) | (0xFFFFFu - lin);
+						amax = max(amax, k);
+					}
+				}
+			}
+			cnt = __reduce_add_sync(0xffffffffu, cnt);
+			tot = __reduce_add_sync(0xffffffffu, tot);
+			sx = __reduce_add_sync(0xffffffffu, sx);
+			sy = __reduce_add_sync(0xffffffffu, sy);
+			amax = __reduce_max_sync(0xffffffffu, amax);
+			if (lane == 0) {
+				atomicAdd(&S.cnt, cnt); atomicAdd(&S.tot, tot);
+				atomicAdd(&S.sx, (unsigned long long)sx); atomicAdd(&S.sy, (unsigned long long)sy);
+				atomicMax(&S.argmax_key, amax);
+			}
+		}
+		__syncthreads();
+		res.kept_points = (int)S.cnt;
+		if (S.tot == 0u) {
+			res.flags |= kFlagEmpty;
+		} else if (a.com_km) {
+			// KMeans(n_clusters=1) == unweighted centroid of the non-zero pixels
+			res.cx = (double)S.sx / (double)S.cnt;
+			res.cy = (double)S.sy / (double)S.cnt;
+		} else {
+			const uint32_t lin = 0xFFFFFu - (S.argmax_key & 0xFFFFFu);
+			res.cx = (double)(lin % (uint32_t)W);
+			res.cy = (double)(lin / (uint32_t)W);
+		}
+
+		// coverage score (a7): max over window positions d in range(L - win) of sum(profile[d:d+win]) / total
+		if (a.cvrg_cfg != nullptr) {
+			const int clip = a.map_clip[m];
+			uint32_t *prof = reinterpret_cast<uint32_t *>(smem + L.pts);  // pts/val are dead now
+			for (int r = 0; r < a.n_ratios; ++r) {
+				const int mode = a.cvrg_cfg[(clip * a.n_ratios + r) * 2 + 0];
+				const int win = a.cvrg_cfg[(clip * a.n_ratios + r) * 2 + 1];
+				const int Lp = (mode == 1) ? W : H;
+				__syncthreads();
+				for (int i = tid; i < Lp; i += NT) {
+					uint32_t s = 0;
+					if (mode == 1) { for (int y = 0; y < H; ++y) s += map8[y * WPS + i]; }
+					else { for (int xw = 0; xw < MWS; ++xw) s += __vsadu4(map32[i * MWS + xw], 0u); }
+					prof[i] = s;
+				}
+				__syncthreads();
+				if (tid == 0) S.argmax_key = 0u;
+				__syncthreads();
+				uint32_t best = 0;
+				for (int d = tid; d < Lp - win; d += NT) {
+					uint32_t s = 0;
+					for (int i = d; i < d + win; ++i) s += prof[i];
+					best = max(best, s);
+				}
+				best = __reduce_max_sync(0xffffffffu, best);
+				if (lane == 0) atomicMax(&S.argmax_key, best);
+				__syncthreads();
+				// t_sum == 0 gives NaN in the reference, which never beats 0.0
+				res.cvrg[r] = (S.tot == 0u) ? 0.0 : ((double)S.argmax_key / (double)S.tot);
+			}
+		}
+
+		if (a.store != nullptr && a.store[m] >= 0) {
+			uint8_t *dst = a.filt + (size_t)a.store[m] * H * a.fstride;
+			const int fw = a.fstride >> 2;
+			for (int i = tid; i < H * fw; i += NT) {
+				const int y = i / fw, xw = i - y * fw;
+				const uint32_t v = (xw < MWS) ? map32[y * MWS + xw] : 0u;
+				*reinterpret_cast<uint32_t *>(dst + (size_t)y * a.fstride + xw * 4) = v;
+			}
+		}
+		if (tid == 0) a.out[m] = res;
+	}
+}
+
+}  // namespace rvb

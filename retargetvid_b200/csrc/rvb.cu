@@ -1,0 +1,911 @@
+// C ABI of the B200-native crop-selection path (include/retargetvid_b200.h): context, workspace,
+// metadata staging and kernel orchestration.  The arithmetic lives in the *.cuh kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/retargetvid_b200.h"
+#include "iou_kernel.cuh"
+#include "map_kernel.cuh"
+#include "track_kernels.cuh"
+
+using namespace rvb;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+
+#define CU(call)                                                                                           \
+	do {                                                                                                   \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess) return fail(RVB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------
+// growable device / pinned buffers
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t need) {
+		if (need <= cap) return RVB_OK;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = need + need / 4 + 4096;
+		CU(cudaMalloc(&p, want));
+		cap = want;
+		return RVB_OK;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct PinBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t need) {
+		if (need <= cap) return RVB_OK;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = need + need / 4 + 4096;
+		CU(cudaMallocHost(&p, want));
+		cap = want;
+		return RVB_OK;
+	}
+	void release() {
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct rvb_ctx {
+	int device = 0;
+	int n_sm = 0;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev_map0 = nullptr, ev_map1 = nullptr, ev_stage = nullptr;
+	bool stage_busy = false;
+	bool map_timed = false;
+	int map_launches = 0;
+	int64_t launches = 0;
+	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
+	PinBuf stage, stage_out;
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory layout of the map kernel for a capacity of nmax points
+// ---------------------------------------------------------------------------------------------
+static int align_up(int v, int a) { return (v + a - 1) / a * a; }
+static const int kMaxDynSmem = 227 * 1024 - 1024;  // per-CTA opt-in limit minus the kernel's static shared memory
+
+static SmemLayout make_layout(int nmax, int H, int WPS, int W) {
+	SmemLayout L;
+	memset(&L, 0, sizeof(L));
+	int o = 0;
+	L.nmax = nmax;
+	L.ncmax = std::min(nmax / 2 + 2, nmax > 4096 ? 770 : 1026);  // bounded by the 227 KB of shared memory
+	L.pts = o; o += align_up(std::max(2 * nmax, 4 * std::max(H, W)), 16);
+	L.val = o; o += align_up(nmax, 16);
+	o = align_up(o, 128);
+	L.u_base = o;
+	L.map = o;
+	int c = o;
+	L.a4 = c; c += 4 * nmax;
+	L.order = c; c += 2 * nmax;
+	L.wp = c; c += 4 * nmax;
+	// d4, rank, pe, pl are contiguous: the occupancy mask of phase 2 aliases them
+	L.d4 = c; c += 4 * nmax;
+	L.rank = c; c += 2 * nmax;
+	L.pe = c; c += 2 * nmax;
+	L.pl = c; c += 2 * nmax;
+	const int mask_bytes = H * ((W + 31) / 32) * 4;
+	if (mask_bytes > 10 * nmax) c = L.d4 + align_up(mask_bytes, 16);
+	L.mask = L.d4;
+	L.queue = c; c += 2 * nmax;
+	L.pnode = L.d4;
+	c = align_up(c, 16);
+	L.cl_stab = c; c += 8 * L.ncmax;
+	L.cl_birth = c; c += 8 * L.ncmax;
+	L.cl_acc = c; c += 4 * L.ncmax;
+	L.cl_parent = c; c += 2 * L.ncmax;
+	L.cl_ch0 = c; c += 2 * L.ncmax;
+	L.cl_ch1 = c; c += 2 * L.ncmax;
+	L.cl_label = c; c += 2 * L.ncmax;
+	L.cl_selanc = c; c += 2 * L.ncmax;
+	const int cluster_end = c;
+	const int map_end = L.map + H * WPS;
+	L.total = align_up(std::max(cluster_end, map_end), 128);
+	return L;
+}
+
+static void build_ring_table(RingTable &t) {
+	struct Off { int d2, dy, dx; };
+	std::vector<Off> offs;
+	for (int dy = -14; dy <= 14; ++dy)
+		for (int dx = -14; dx <= 14; ++dx) {
+			const int d2 = dy * dy + dx * dx;
+			if (d2 > 0 && d2 <= kRingD2Max) offs.push_back({d2, dy, dx});
+		}
+	std::stable_sort(offs.begin(), offs.end(), [](const Off &a, const Off &b) { return a.d2 < b.d2; });
+	memset(&t, 0, sizeof(t));
+	int nr = 0;
+	for (size_t i = 0; i < offs.size(); ++i) {
+		t.dy[i] = (int8_t)offs[i].dy;
+		t.dx[i] = (int8_t)offs[i].dx;
+		if (i + 1 == offs.size() || offs[i + 1].d2 != offs[i].d2) {
+			t.ring_end[nr] = (uint16_t)(i + 1);
+			t.ring_d2[nr] = (uint16_t)offs[i].d2;
+			++nr;
+		}
+	}
+	t.n_rings = nr;
+	t.n_offsets = (int)offs.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Butterworth low-pass design: scipy.signal.butter(order, Wn, 'lowpass') -> (b, a), and
+// scipy.signal.lfilter_zi(b, a) -- the calls made at smartVidCrop.py:1601-1605 (via filtfilt).
+// ---------------------------------------------------------------------------------------------
+static void butter_design(int order, double wn, FilterCoef &fc) {
+	memset(&fc, 0, sizeof(fc));
+	if (!(wn > 0.0 && wn < 1.0) || order < 1 || order > RVB_MAX_LP_ORDER) {
+		fc.order = 0;  // scipy raises -> the reference falls back to moving averages
+		return;
+	}
+	typedef std::complex<double> cd;
+	const double pi = 3.14159265358979323846;
+	// buttap: poles of the analog prototype
+	std::vector<cd> p(order);
+	for (int i = 0; i < order; ++i) {
+		const int m = -order + 1 + 2 * i;
+		p[i] = -std::exp(cd(0.0, pi * m / (2.0 * order)));
+	}
+	double k = 1.0;
+	// pre-warp (fs = 2), lp2lp_zpk
+	const double fs = 2.0;
+	const double warped = 2.0 * fs * tan(pi * wn / fs);
+	for (auto &v : p) v *= warped;
+	k *= pow(warped, (double)order);
+	// bilinear_zpk
+	const double fs2 = 2.0 * fs;
+	cd den(1.0, 0.0);
+	std::vector<cd> pz(order);
+	for (int i = 0; i < order; ++i) {
+		pz[i] = (fs2 + p[i]) / (fs2 - p[i]);
+		den *= (fs2 - p[i]);
+	}
+	const double kz = k * (cd(1.0, 0.0) / den).real();
+	// zpk2tf: zeros are all at -1
+	std::vector<cd> a(1, cd(1.0, 0.0)), b(1, cd(1.0, 0.0));
+	for (int i = 0; i < order; ++i) {
+		std::vector<cd> na(a.size() + 1, cd(0.0, 0.0)), nb(b.size() + 1, cd(0.0, 0.0));
+		for (size_t j = 0; j < a.size(); ++j) {
+			na[j] += a[j];
+			na[j + 1] -= a[j] * pz[i];
+			nb[j] += b[j];
+			nb[j + 1] += b[j];  // (z - (-1))
+		}
+		a = na;
+		b = nb;
+	}
+	fc.order = order;
+	for (int i = 0; i <= order; ++i) {
+		fc.a[i] = a[i].real();
+		fc.b[i] = kz * b[i].real();
+	}
+	// lfilter_zi: solve (I - A^T) zi = b[1:] - a[1:] b[0] with the companion matrix of a (a[0] == 1)
+	double asum = 1.0, bsum = 0.0;
+	for (int i = 1; i <= order; ++i) {
+		asum += fc.a[i];
+		bsum += fc.b[i] - fc.a[i] * fc.b[0];
+	}
+	fc.zi[0] = bsum / asum;
+	double as = 1.0, cs = 0.0;
+	for (int i = 1; i < order; ++i) {
+		as += fc.a[i];
+		cs += fc.b[i] - fc.a[i] * fc.b[0];
+		fc.zi[i] = as * fc.zi[0] - cs;
+	}
+}
+
+// sc_calc_dest_size -- smartVidCrop.py:946-977
+static void calc_dest_size(int w_orig, int h_orig, double tw, double th, int out[3]) {
+	const double orig_ratio = (double)w_orig / (double)h_orig;
+	const double target_ratio = tw / th;
+	if (fabs(orig_ratio - target_ratio) < 0.0000001) {
+		out[0] = 0; out[1] = w_orig; out[2] = h_orig;
+		return;
+	}
+	int w_final = (int)floor((tw / th) * h_orig);
+	int h_final = h_orig;
+	int mode = 1;
+	if (w_final > w_orig || h_final > h_orig) {
+		w_final = w_orig;
+		h_final = (int)floor((th / tw) * w_orig);
+		mode = 2;
+	}
+	out[0] = mode; out[1] = w_final; out[2] = h_final;
+}
+
+// ---------------------------------------------------------------------------------------------
+// API
+// ---------------------------------------------------------------------------------------------
+extern "C" const char *rvb_version(void) { return "retargetvid_b200 0.1.0 (smartVidCrop 1.4.0 hot path, sm_100a)"; }
+extern "C" const char *rvb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
+	if (!out) return fail(RVB_ERR_INVALID, "rvb_ctx_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	CU(cudaGetDeviceCount(&n));
+	if (device < 0 || device >= n) return fail(RVB_ERR_INVALID, "rvb_ctx_create: device %d of %d", device, n);
+	CU(cudaSetDevice(device));
+	rvb_ctx *c = new rvb_ctx();
+	c->device = device;
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	c->n_sm = prop.multiProcessorCount;
+	CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	c->stream = c->own_stream;
+	CU(cudaEventCreate(&c->ev_map0));
+	CU(cudaEventCreate(&c->ev_map1));
+	CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+	RingTable t;
+	build_ring_table(t);
+	CU(cudaMemcpyToSymbol(c_rings, &t, sizeof(t)));
+	CU(cudaFuncSetAttribute(map_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+	*out = c;
+	return RVB_OK;
+}
+
+extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
+	if (!c) return RVB_OK;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	DevBuf *bufs[] = {&c->maps_in, &c->maps_nhw, &c->filt, &c->meta, &c->mapout, &c->series, &c->scratch,
+					  &c->boxes, &c->misc, &c->iou_a, &c->iou_b, &c->iou_c};
+	for (DevBuf *b : bufs) b->release();
+	c->stage.release();
+	c->stage_out.release();
+	if (c->ev_map0) cudaEventDestroy(c->ev_map0);
+	if (c->ev_map1) cudaEventDestroy(c->ev_map1);
+	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	delete c;
+	return RVB_OK;
+}
+
+extern "C" int rvb_ctx_set_stream(rvb_ctx *c, void *stream) {
+	if (!c) return fail(RVB_ERR_INVALID, "ctx is NULL");
+	c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+	return RVB_OK;
+}
+
+extern "C" int rvb_ctx_synchronize(rvb_ctx *c) {
+	if (!c) return fail(RVB_ERR_INVALID, "ctx is NULL");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	return RVB_OK;
+}
+
+extern "C" int64_t rvb_ctx_launch_count(const rvb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int rvb_ctx_last_map_kernel_ms(rvb_ctx *c, float *ms, int32_t *launches) {
+	if (!c) return fail(RVB_ERR_INVALID, "ctx is NULL");
+	if (!c->map_timed) return fail(RVB_ERR_INVALID, "no crop_track call has run on this context");
+	CU(cudaEventSynchronize(c->ev_map1));
+	float t = 0.f;
+	CU(cudaEventElapsedTime(&t, c->ev_map0, c->ev_map1));
+	if (ms) *ms = t;
+	if (launches) *launches = c->map_launches;
+	return RVB_OK;
+}
+
+extern "C" int rvb_params_default(rvb_params *p, int use_best_settings) {
+	if (!p) return fail(RVB_ERR_INVALID, "params is NULL");
+	memset(p, 0, sizeof(*p));
+	p->t_threshold = 120; p->clust_filt = 1; p->hdbscan_min = 26; p->hdbscan_min_samples = 0;
+	p->select_sum = 2; p->op_close = 1; p->com_km = 1; p->t_border = -1;
+	p->loess_filt = 1; p->loess_degree = 2; p->lp_filt = 1; p->lp_order = 5; p->shift_time = 0;
+	p->exit_on_low_cvrg = 0; p->cvrg_window = 0;
+	p->loess_w_secs = 2.0; p->lp_cutoff = 2.0; p->resize_factor = 1.0; p->t_cvrg = 0.60;
+	if (use_best_settings) {
+		p->t_threshold = 90; p->hdbscan_min = 5; p->hdbscan_min_samples = 3; p->resize_factor = 4.0;
+		p->select_sum = 1; p->lp_cutoff = 1.0; p->lp_order = 2; p->loess_filt = 0;
+	}
+	return RVB_OK;
+}
+
+// one launch of the map kernel family
+template <int NT, int TPT>
+static int launch_map(rvb_ctx *c, MapArgs a, int H, int W, int WPS, int grid) {
+	a.lay = make_layout(NT * TPT, H, WPS, W);
+	if (a.lay.total > (NT * TPT > 4096 ? kMaxDynSmem : 200 * 1024)) return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d needs %d B of shared memory", H, W, a.lay.total);
+	map_kernel<NT, TPT><<<grid, NT, a.lay.total, c->stream>>>(a);
+	CU(cudaGetLastError());
+	c->launches += 1;
+	c->map_launches += 1;
+	return RVB_OK;
+}
+
+template <int NT, int TPT>
+static int occupancy_grid(rvb_ctx *c, int smem, int n_items) {
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_kernel<NT, TPT>, NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+	int g = c->n_sm * per_sm;
+	if (n_items >= 0) g = std::min(g, std::max(n_items, 1));
+	return std::max(g, 1);
+}
+
+namespace {
+struct Staging {  // packs the small per-call arrays into one pinned block -> one H2D copy
+	std::vector<uint8_t> bytes;
+	size_t add(const void *src, size_t n) {
+		size_t off = (bytes.size() + 255) / 256 * 256;
+		bytes.resize(off + n);
+		if (src && n) memcpy(bytes.data() + off, src, n);
+		return off;
+	}
+};
+}  // namespace
+
+extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_batch *b) {
+	if (!c || !p || !b) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (p->resize_factor != 1.0)
+		return fail(RVB_ERR_UNSUPPORTED, "resize_factor=%g: only 1.0 is built (SURVEY.md 8f)", p->resize_factor);
+	if (b->n_clips <= 0) return fail(RVB_ERR_INVALID, "n_clips=%d", b->n_clips);
+	if (b->n_ratios < 1 || b->n_ratios > RVB_MAX_RATIOS) return fail(RVB_ERR_INVALID, "n_ratios=%d", b->n_ratios);
+	const int H = b->h_process, W = b->w_process;
+	if (H < 1 || W < 1 || H > 256 || W > 256) return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d (max 256x256)", H, W);
+	if (p->hdbscan_min < 2) return fail(RVB_ERR_INVALID, "hdbscan_min=%d (min_cluster_size must be >= 2)", p->hdbscan_min);
+	if (p->loess_degree < 1 || p->loess_degree > 2) return fail(RVB_ERR_UNSUPPORTED, "loess_degree=%d", p->loess_degree);
+	if (!b->clips || !b->shots || !b->true_inds || (!b->maps && !b->clip_maps) || !b->boxes) return fail(RVB_ERR_INVALID, "NULL array in batch");
+	if (p->t_border != -1 && b->maps_kind == RVB_MAPS_F32_NHW)
+		return fail(RVB_ERR_UNSUPPORTED, "border detection on float32 maps is not built");
+	CU(cudaSetDevice(c->device));
+	const int WPS = align_up(W, 16);
+	const int R = b->n_ratios;
+	const bool host = b->mem_space == RVB_MEM_HOST;
+	cudaStream_t st = c->stream;
+
+	// ---- metadata --------------------------------------------------------------------------------
+	const int nc = b->n_clips;
+	long long tot_maps = 0, tot_frames = 0, tot_shots = 0;
+	for (int i = 0; i < nc; ++i) {
+		const rvb_clip &cl = b->clips[i];
+		if (cl.n_maps < 1 || cl.n_frames < 1 || cl.n_shots < 1) return fail(RVB_ERR_INVALID, "clip %d is empty", i);
+		if (cl.map_offset != tot_maps || cl.frame_offset != tot_frames || cl.shot_offset != tot_shots)
+			return fail(RVB_ERR_INVALID, "clip %d: offsets must be the running sums (packed arrays)", i);
+		tot_maps += cl.n_maps; tot_frames += cl.n_frames; tot_shots += cl.n_shots;
+	}
+	if (tot_maps > 0x7fffffffLL / 64 || tot_frames > 0x3fffffffLL) return fail(RVB_ERR_INVALID, "batch too large");
+	const int NM = (int)tot_maps, NF = (int)tot_frames, NS = (int)tot_shots;
+
+	std::vector<ClipDev> clips(nc);
+	std::vector<ShotDev> shots(NS);
+	std::vector<int> frame_shot(NF), frame_clip(NF), map_clip(NM), pred(NM, -1), store(NM, -1), depth(NM, 0);
+	std::vector<int> clip_final(nc * R * 3), cvrg_cfg(nc * R * 2), clip_coef(nc);
+	std::vector<FilterCoef> coefs;
+	std::vector<double> coef_fr;
+	long long scratch_doubles = 0;
+	int n_slots = 0;
+	const bool want_filtered = b->filtered_maps != nullptr;
+	for (int i = 0; i < nc; ++i) {
+		const rvb_clip &cl = b->clips[i];
+		ClipDev &d = clips[i];
+		d.n_maps = cl.n_maps; d.n_frames = cl.n_frames; d.n_shots = cl.n_shots;
+		d.h_orig = cl.h_orig; d.w_orig = cl.w_orig; d.fr = cl.fr;
+		d.map_offset = (int)cl.map_offset; d.frame_offset = (int)cl.frame_offset; d.shot_offset = (int)cl.shot_offset;
+		for (int k = 0; k < cl.n_maps; ++k) map_clip[d.map_offset + k] = i;
+		for (int k = 0; k < cl.n_frames; ++k) frame_clip[d.frame_offset + k] = i;
+		std::vector<char> is_cut(cl.n_maps + 2, 0);
+		for (int s = 0; s < cl.n_shots; ++s) {
+			const int32_t *row = b->shots + (cl.shot_offset + s) * 4;
+			ShotDev &sh = shots[d.shot_offset + s];
+			sh.f0 = row[0]; sh.f1 = row[1]; sh.m0 = row[2]; sh.m1 = row[3]; sh.clip = i;
+			if (sh.f0 < 0 || sh.f1 >= cl.n_frames || sh.f1 < sh.f0 || sh.m0 < 0 || sh.m1 >= cl.n_maps || sh.m1 < sh.m0)
+				return fail(RVB_ERR_INVALID, "clip %d shot %d: bad range", i, s);
+			if (s == 0 ? (sh.f0 != 0) : (sh.f0 != shots[d.shot_offset + s - 1].f1 + 1))
+				return fail(RVB_ERR_INVALID, "clip %d shot %d: shots must tile the frames", i, s);
+			sh.frame_base = d.frame_offset + sh.f0;
+			sh.map_base = d.map_offset + sh.m0;
+			const int n = sh.m1 - sh.m0 + 1, clen = sh.f1 - sh.f0 + 1;
+			const long long need = std::max<long long>(8LL * n + 3, 2LL * (clen + 6 * (RVB_MAX_LP_ORDER + 1)));
+			sh.scratch_base = (int)scratch_doubles;
+			scratch_doubles += need;
+			for (int f = sh.f0; f <= sh.f1; ++f) frame_shot[d.frame_offset + f] = d.shot_offset + s;
+			is_cut[sh.m0] = 1;                                     // segm_cuts: shot starts ...
+			if (s == cl.n_shots - 1) is_cut[sh.m1] = 1;            // ... + the last end (smartVidCrop.py:2324-2327)
+		}
+		if (shots[d.shot_offset + cl.n_shots - 1].f1 != cl.n_frames - 1)
+			return fail(RVB_ERR_INVALID, "clip %d: last shot must end at the last frame", i);
+		// cut-adjacent blend (smartVidCrop.py:2369-2373): map k+1 <- (map k+1 + filtered map k) / 2
+		if (p->clust_filt) {
+			for (int k = 0; k < cl.n_maps - 2; ++k) {
+				const bool hit = (k >= 1 && is_cut[k - 1]) || is_cut[k] || is_cut[k + 1];
+				if (hit) {
+					const int src = d.map_offset + k, dst = src + 1;
+					if (store[src] < 0) store[src] = n_slots++;
+					pred[dst] = store[src];
+					depth[dst] = depth[src] + 1;
+				}
+			}
+		}
+		if (want_filtered)
+			for (int k = 0; k < cl.n_maps; ++k) if (store[d.map_offset + k] < 0) store[d.map_offset + k] = n_slots++;
+		for (int r = 0; r < R; ++r) {
+			int fin[3];
+			calc_dest_size(cl.w_orig, cl.h_orig, b->ratio_w[r], b->ratio_h[r], fin);
+			memcpy(&clip_final[(i * R + r) * 3], fin, sizeof(fin));
+			int win;
+			if (fin[0] == 1) win = p->cvrg_window ? (int)((double)fin[1] * W / cl.w_orig) : W;
+			else win = p->cvrg_window ? (int)((double)fin[2] * H / cl.h_orig) : H;
+			cvrg_cfg[(i * R + r) * 2 + 0] = fin[0];
+			cvrg_cfg[(i * R + r) * 2 + 1] = win;
+		}
+		// one Butterworth design per distinct frame rate
+		int ci = -1;
+		for (size_t k = 0; k < coef_fr.size(); ++k) if (coef_fr[k] == cl.fr) ci = (int)k;
+		if (ci < 0) {
+			FilterCoef fc;
+			butter_design(p->lp_order, p->lp_cutoff / (0.5 * cl.fr), fc);
+			coefs.push_back(fc);
+			coef_fr.push_back(cl.fr);
+			ci = (int)coefs.size() - 1;
+		}
+		clip_coef[i] = ci;
+	}
+	if (scratch_doubles > 0x7fffffffLL) return fail(RVB_ERR_INVALID, "batch too large (scratch)");
+	int max_depth = 0;
+	for (int v : depth) max_depth = std::max(max_depth, v);
+	const int n_waves = max_depth + 1;
+	std::vector<std::vector<int>> waves(n_waves);
+	for (int m = 0; m < NM; ++m) waves[depth[m]].push_back(m);
+
+	// counters: per wave and capacity class {head, len} of that class's work list
+	// layout of `counters`: [wave][class 0..3][2] ints
+	std::vector<int> counters(n_waves * 4 * 2, 0);
+	for (int w = 0; w < n_waves; ++w) counters[(w * 4 + 0) * 2 + 1] = (int)waves[w].size();
+
+	Staging sg;
+	const size_t o_clips = sg.add(clips.data(), clips.size() * sizeof(ClipDev));
+	const size_t o_shots = sg.add(shots.data(), shots.size() * sizeof(ShotDev));
+	const size_t o_ti = sg.add(b->true_inds, (size_t)NM * sizeof(int));
+	const size_t o_fshot = sg.add(frame_shot.data(), (size_t)NF * sizeof(int));
+	const size_t o_fclip = sg.add(frame_clip.data(), (size_t)NF * sizeof(int));
+	const size_t o_mclip = sg.add(map_clip.data(), (size_t)NM * sizeof(int));
+	const size_t o_pred = sg.add(pred.data(), (size_t)NM * sizeof(int));
+	const size_t o_store = sg.add(store.data(), (size_t)NM * sizeof(int));
+	const size_t o_final = sg.add(clip_final.data(), clip_final.size() * sizeof(int));
+	const size_t o_cvrg = sg.add(cvrg_cfg.data(), cvrg_cfg.size() * sizeof(int));
+	const size_t o_ccoef = sg.add(clip_coef.data(), clip_coef.size() * sizeof(int));
+	const size_t o_coefs = sg.add(coefs.data(), coefs.size() * sizeof(FilterCoef));
+	const size_t o_cnt = sg.add(counters.data(), counters.size() * sizeof(int));
+	std::vector<size_t> o_wave(n_waves), o_ovf1(n_waves), o_ovf2(n_waves), o_ovf3(n_waves);
+	for (int w = 0; w < n_waves; ++w) {
+		o_wave[w] = sg.add(waves[w].data(), waves[w].size() * sizeof(int));
+		o_ovf1[w] = sg.add(nullptr, waves[w].size() * sizeof(int));
+		o_ovf2[w] = sg.add(nullptr, waves[w].size() * sizeof(int));
+		o_ovf3[w] = sg.add(nullptr, waves[w].size() * sizeof(int));
+	}
+	const size_t o_borders = sg.add(nullptr, (size_t)nc * 4 * sizeof(int));
+	const size_t o_status = sg.add(nullptr, (size_t)nc * sizeof(int));
+	const size_t o_prof = sg.add(nullptr, (size_t)nc * (H + W) * sizeof(uint32_t));
+	const size_t o_dims = sg.add(nullptr, (size_t)nc * R * 9 * sizeof(int));
+	const size_t o_cscore = sg.add(nullptr, (size_t)nc * (1 + R) * sizeof(double));
+	const size_t o_mscore = sg.add(nullptr, (size_t)NM * sizeof(double));
+	const size_t o_minfo = sg.add(nullptr, (size_t)NM * 4 * sizeof(int));
+	const size_t o_empty = sg.add(nullptr, (size_t)NM);
+	const size_t meta_bytes = sg.bytes.size();
+	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
+	if (c->stage.ensure(meta_bytes)) return RVB_ERR_CUDA;
+	if (c->meta.ensure(meta_bytes)) return RVB_ERR_CUDA;
+	memcpy(c->stage.p, sg.bytes.data(), meta_bytes);
+	CU(cudaMemcpyAsync(c->meta.p, c->stage.p, meta_bytes, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->ev_stage, st));
+	c->stage_busy = true;
+	uint8_t *M = (uint8_t *)c->meta.p;
+	const ClipDev *d_clips = (const ClipDev *)(M + o_clips);
+	const ShotDev *d_shots = (const ShotDev *)(M + o_shots);
+	const int *d_ti = (const int *)(M + o_ti);
+	const int *d_fshot = (const int *)(M + o_fshot);
+	const int *d_fclip = (const int *)(M + o_fclip);
+	int *d_cnt = (int *)(M + o_cnt);
+	int *d_borders = (int *)(M + o_borders);
+	int *d_status = (int *)(M + o_status);
+	uint32_t *d_prof = (uint32_t *)(M + o_prof);
+
+	// ---- maps ------------------------------------------------------------------------------------
+	const uint8_t *d_u8 = nullptr;
+	const float *d_f32 = nullptr;
+	int gstride = WPS;
+	size_t bytes_per_map;
+	if (b->maps_kind == RVB_MAPS_F32_NHW) bytes_per_map = (size_t)H * W * sizeof(float);
+	else if (b->maps_kind == RVB_MAPS_U8_NHW) {
+		if (b->row_stride < W || (b->row_stride % 4) != 0) return fail(RVB_ERR_INVALID, "row_stride=%d", b->row_stride);
+		gstride = b->row_stride;
+		bytes_per_map = (size_t)H * gstride;
+	} else if (b->maps_kind == RVB_MAPS_U8_HWN) bytes_per_map = (size_t)H * W;
+	else return fail(RVB_ERR_INVALID, "maps_kind=%d", b->maps_kind);
+	const void *d_in = b->maps;
+	if (host || b->clip_maps) {
+		// gather into one device block (H2D from host memory, or D2D from per-clip device blocks)
+		if (c->maps_in.ensure((size_t)NM * bytes_per_map)) return RVB_ERR_CUDA;
+		const cudaMemcpyKind k = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+		if (b->clip_maps) {
+			for (int i = 0; i < nc; ++i) {
+				if (!b->clip_maps[i]) return fail(RVB_ERR_INVALID, "clip_maps[%d] is NULL", i);
+				CU(cudaMemcpyAsync((uint8_t *)c->maps_in.p + (size_t)clips[i].map_offset * bytes_per_map, b->clip_maps[i],
+								   (size_t)clips[i].n_maps * bytes_per_map, k, st));
+			}
+		} else {
+			CU(cudaMemcpyAsync(c->maps_in.p, b->maps, (size_t)NM * bytes_per_map, k, st));
+		}
+		d_in = c->maps_in.p;
+	}
+	if (b->maps_kind == RVB_MAPS_F32_NHW) {
+		d_f32 = (const float *)d_in;
+		if (((uintptr_t)d_f32 & 15) != 0) return fail(RVB_ERR_INVALID, "maps must be 16-byte aligned");
+	} else if (b->maps_kind == RVB_MAPS_U8_NHW) {
+		d_u8 = (const uint8_t *)d_in;
+		if (((uintptr_t)d_u8 & 15) != 0) return fail(RVB_ERR_INVALID, "maps must be 16-byte aligned");
+	} else {
+		const uint8_t *src = (const uint8_t *)d_in;
+		if (c->maps_nhw.ensure((size_t)NM * H * WPS)) return RVB_ERR_CUDA;
+		CU(cudaMemsetAsync(c->maps_nhw.p, 0, (size_t)NM * H * WPS, st));
+		for (int i = 0; i < nc; ++i) {
+			const ClipDev &d = clips[i];
+			dim3 grid((d.n_maps + 31) / 32, (H * W + 31) / 32), block(32, 8);
+			transpose_hwn_kernel<<<grid, block, 0, st>>>(src + (size_t)d.map_offset * H * W, H, W, d.n_maps,
+														 (uint8_t *)c->maps_nhw.p + (size_t)d.map_offset * H * WPS, WPS);
+			c->launches += 1;
+		}
+		CU(cudaGetLastError());
+		d_u8 = (const uint8_t *)c->maps_nhw.p;
+		gstride = WPS;
+	}
+
+	// ---- border profiles ---------------------------------------------------------------------------
+	CU(cudaMemsetAsync(d_prof, 0, (size_t)nc * (H + W) * sizeof(uint32_t), st));
+	if (p->t_border != -1) {
+		border_profile_kernel<<<NM, 128, 0, st>>>(d_u8, H, W, gstride, (const int *)(M + o_mclip), d_prof);
+		CU(cudaGetLastError());
+		c->launches += 1;
+	}
+	border_finish_kernel<<<(nc + 127) / 128, 128, 0, st>>>(d_clips, nc, d_prof, H, W, p->t_border, d_borders);
+	CU(cudaGetLastError());
+	c->launches += 1;
+
+	// ---- the fused map kernel, wave by wave, three capacity classes each ---------------------------
+	if (c->mapout.ensure((size_t)NM * sizeof(MapOut))) return RVB_ERR_CUDA;
+	if (n_slots > 0 && c->filt.ensure((size_t)n_slots * H * WPS)) return RVB_ERR_CUDA;
+	MapArgs a;
+	memset(&a, 0, sizeof(a));
+	a.maps_u8 = d_u8; a.maps_f32 = d_f32; a.H = H; a.W = W; a.WPS = WPS; a.gstride = gstride;
+	a.pred = (const int *)(M + o_pred); a.store = (const int *)(M + o_store); a.map_clip = (const int *)(M + o_mclip);
+	a.filt = (uint8_t *)c->filt.p; a.fstride = WPS; a.out = (MapOut *)c->mapout.p;
+	a.border_prof = nullptr;
+	a.cvrg_cfg = p->exit_on_low_cvrg ? (const int *)(M + o_cvrg) : nullptr;
+	a.n_ratios = R; a.labels_dbg = nullptr;
+	a.t_threshold = p->t_threshold; a.clust_filt = p->clust_filt; a.mcs = p->hdbscan_min;
+	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
+	c->map_launches = 0;
+	CU(cudaEventRecord(c->ev_map0, st));
+	for (int w = 0; w < n_waves; ++w) {
+		const int nw = (int)waves[w].size();
+		int *cnt = d_cnt + (w * 4) * 2;
+		// capacity classes 1024 / 2048 / 4096 / 8192 salient pixels: a map that does not fit is
+		// appended to the next class's list by the kernel itself (no host round trip)
+		a.list = (const int *)(M + o_wave[w]); a.head = cnt + 0; a.list_len = cnt + 1;
+		a.ovf_list = (int *)(M + o_ovf1[w]); a.ovf_len = cnt + 3;
+		int rc = launch_map<256, 4>(c, a, H, W, WPS, occupancy_grid<256, 4>(c, make_layout(1024, H, WPS, W).total, nw));
+		if (rc) return rc;
+		a.list = (const int *)(M + o_ovf1[w]); a.head = cnt + 2; a.list_len = cnt + 3;
+		a.ovf_list = (int *)(M + o_ovf2[w]); a.ovf_len = cnt + 5;
+		rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W).total, nw));
+		if (rc) return rc;
+		a.list = (const int *)(M + o_ovf2[w]); a.head = cnt + 4; a.list_len = cnt + 5;
+		a.ovf_list = (int *)(M + o_ovf3[w]); a.ovf_len = cnt + 7;
+		rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W).total, nw));
+		if (rc) return rc;
+		// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
+		a.list = (const int *)(M + o_ovf3[w]); a.head = cnt + 6; a.list_len = cnt + 7;
+		a.ovf_list = nullptr; a.ovf_len = nullptr;
+		rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W).total, nw));
+		if (rc) return rc;
+	}
+	CU(cudaEventRecord(c->ev_map1, st));
+	c->map_timed = true;
+
+	// ---- centre track ------------------------------------------------------------------------------
+	// series: dx, dy [NM]; dxi, dyi, dxl, dyl, dxs, dys [NF]
+	if (c->series.ensure(((size_t)2 * NM + (size_t)6 * NF) * sizeof(double))) return RVB_ERR_CUDA;
+	double *d_dx = (double *)c->series.p, *d_dy = d_dx + NM;
+	double *d_ser = d_dy + NM;  // [6][NF]
+	double *d_dxi = d_ser, *d_dyi = d_ser + NF, *d_dxl = d_ser + 2 * (size_t)NF, *d_dyl = d_ser + 3 * (size_t)NF;
+	double *d_dxs = d_ser + 4 * (size_t)NF, *d_dys = d_ser + 5 * (size_t)NF;
+	if (c->scratch.ensure((size_t)std::max<long long>(scratch_doubles, 1) * sizeof(double))) return RVB_ERR_CUDA;
+	double *d_scratch = (double *)c->scratch.p;
+	if (c->boxes.ensure((size_t)R * NF * 4 * sizeof(int32_t))) return RVB_ERR_CUDA;
+	int32_t *d_boxes = host ? (int32_t *)c->boxes.p : b->boxes;
+	const MapOut *d_mo = (const MapOut *)c->mapout.p;
+	uint8_t *d_empty = M + o_empty;
+
+	fill_centres_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_shots, d_mo, d_dx, d_dy, d_empty, d_status);
+	spline_setup_kernel<<<(NS + 63) / 64, 64, 0, st>>>(d_shots, NS, d_ti, d_dx, d_dy, d_scratch);
+	interp_eval_kernel<<<(NF + 255) / 256, 256, 0, st>>>(d_shots, d_fshot, NF, d_ti, d_dx, d_dy, d_scratch, d_dxi, d_dyi);
+	lowpass_kernel<<<(2 * NS + 63) / 64, 64, 0, st>>>(d_shots, NS, d_clips, (const FilterCoef *)(M + o_coefs),
+													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt);
+	{
+		const long long warps = 2LL * NF;
+		const int blocks = (int)((warps * 32 + 255) / 256);
+		smooth_kernel<<<blocks, 256, 0, st>>>(d_shots, d_fshot, NF, d_clips, d_dxl, d_dyl, d_dxs, d_dys, p->loess_filt,
+											  p->loess_w_secs, p->loess_degree);
+	}
+	int32_t *d_dims = (int32_t *)(M + o_dims);
+	boxes_kernel<<<(int)(((long long)NF * R + 255) / 256), 256, 0, st>>>(d_clips, d_fclip, NF, R, (const int *)(M + o_final),
+																		d_borders, H, W, d_dxs, d_dys, p->shift_time, d_boxes, d_dims);
+	double *d_cscore = (double *)(M + o_cscore), *d_mscore = (double *)(M + o_mscore);
+	clip_scores_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_mo, H, W, R, d_mscore, d_cscore);
+	CU(cudaGetLastError());
+	c->launches += 7;
+
+	// ---- results -----------------------------------------------------------------------------------
+	const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+	if (host) CU(cudaMemcpyAsync(b->boxes, d_boxes, (size_t)R * NF * 4 * sizeof(int32_t), kind, st));
+	if (b->centres) CU(cudaMemcpyAsync(b->centres, d_dx, (size_t)2 * NM * sizeof(double), kind, st));
+	if (b->empty) CU(cudaMemcpyAsync(b->empty, d_empty, (size_t)NM, kind, st));
+	if (b->series) CU(cudaMemcpyAsync(b->series, d_ser, (size_t)6 * NF * sizeof(double), kind, st));
+	if (b->map_scores) CU(cudaMemcpyAsync(b->map_scores, d_mscore, (size_t)NM * sizeof(double), kind, st));
+	if (b->clip_scores) CU(cudaMemcpyAsync(b->clip_scores, d_cscore, (size_t)nc * (1 + R) * sizeof(double), kind, st));
+	if (b->clip_dims) CU(cudaMemcpyAsync(b->clip_dims, d_dims, (size_t)nc * R * 9 * sizeof(int), kind, st));
+	if (b->clip_status) CU(cudaMemcpyAsync(b->clip_status, d_status, (size_t)nc * sizeof(int), kind, st));
+	if (b->map_info) {
+		// n_points, n_clusters, kept_points, flags are 4 consecutive ints inside MapOut
+		CU(cudaMemcpy2DAsync(b->map_info, 4 * sizeof(int), (const uint8_t *)d_mo + offsetof(MapOut, n_points), sizeof(MapOut),
+							 4 * sizeof(int), NM, kind, st));
+	}
+	if (want_filtered) {
+		const int so = b->row_stride_out > 0 ? b->row_stride_out : WPS;
+		if (so < W) return fail(RVB_ERR_INVALID, "row_stride_out=%d", so);
+		// slots were handed out in map order when filtered maps are requested only if no blend slot came first,
+		// so copy map by map through the slot table
+		for (int m = 0; m < NM; ++m)
+			CU(cudaMemcpy2DAsync(b->filtered_maps + (size_t)m * H * so, so, (const uint8_t *)c->filt.p + (size_t)store[m] * H * WPS,
+								 WPS, W, H, kind, st));
+	}
+	if (host) {
+		std::vector<int> status(nc);
+		CU(cudaMemcpyAsync(status.data(), d_status, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		for (int i = 0; i < nc; ++i)
+			if (status[i] != RVB_OK)
+				return fail(status[i], "clip %d: %s", i,
+							status[i] == RVB_ERR_CAPACITY ? "a map has more salient pixels than RVB_MAX_POINTS"
+														  : "no map with a salient pixel (the reference raises TypeError in interp_handler)");
+	}
+	return RVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// IoU
+// ---------------------------------------------------------------------------------------------
+extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
+	if (!c || !b) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (b->n_videos < 1 || b->n_users < 1 || b->n_users > 64) return fail(RVB_ERR_INVALID, "n_videos=%d n_users=%d", b->n_videos, b->n_users);
+	if (!b->frame_offset || !b->n_eval || !b->method_boxes || !b->annot_boxes || !b->acc) return fail(RVB_ERR_INVALID, "NULL array");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const bool host = b->mem_space == RVB_MEM_HOST;
+	const int V = b->n_videos, U = b->n_users;
+	const long long NF = b->frame_offset[V];
+	if (NF < 1 || b->frame_offset[0] != 0) return fail(RVB_ERR_INVALID, "frame_offset must start at 0");
+	std::vector<int> frame_video((size_t)NF), first(V), neval(V);
+	for (int v = 0; v < V; ++v) {
+		const long long f0 = b->frame_offset[v], f1 = b->frame_offset[v + 1];
+		if (f1 < f0) return fail(RVB_ERR_INVALID, "frame_offset not monotone");
+		if (b->n_eval[v] < 1 || b->n_eval[v] > f1 - f0) return fail(RVB_ERR_INVALID, "video %d: n_eval=%d of %lld frames", v, b->n_eval[v], f1 - f0);
+		first[v] = (int)f0;
+		neval[v] = b->n_eval[v];
+		for (long long f = f0; f < f1; ++f) frame_video[(size_t)f] = v;
+	}
+	Staging sg;
+	const size_t o_fv = sg.add(frame_video.data(), (size_t)NF * sizeof(int));
+	const size_t o_first = sg.add(first.data(), (size_t)V * sizeof(int));
+	const size_t o_ne = sg.add(neval.data(), (size_t)V * sizeof(int));
+	const size_t o_acc = sg.add(nullptr, (size_t)V * U * 2 * sizeof(uint64_t));
+	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
+	if (c->stage.ensure(sg.bytes.size()) || c->iou_a.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
+	memcpy(c->stage.p, sg.bytes.data(), sg.bytes.size());
+	CU(cudaMemcpyAsync(c->iou_a.p, c->stage.p, sg.bytes.size(), cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->ev_stage, st));
+	c->stage_busy = true;
+	uint8_t *M = (uint8_t *)c->iou_a.p;
+	const int32_t *d_method = b->method_boxes, *d_annot = b->annot_boxes;
+	double *d_fiou = b->frame_iou;
+	const size_t mb = (size_t)NF * 4 * sizeof(int32_t);
+	if (host) {
+		if (c->iou_b.ensure(mb * (1 + U))) return RVB_ERR_CUDA;
+		CU(cudaMemcpyAsync(c->iou_b.p, b->method_boxes, mb, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync((uint8_t *)c->iou_b.p + mb, b->annot_boxes, mb * U, cudaMemcpyHostToDevice, st));
+		d_method = (const int32_t *)c->iou_b.p;
+		d_annot = (const int32_t *)((uint8_t *)c->iou_b.p + mb);
+		if (b->frame_iou) {
+			if (c->iou_c.ensure((size_t)NF * U * sizeof(double))) return RVB_ERR_CUDA;
+			d_fiou = (double *)c->iou_c.p;
+		}
+	}
+	unsigned long long *d_acc = (unsigned long long *)(M + o_acc);
+	CU(cudaMemsetAsync(d_acc, 0, (size_t)V * U * 2 * sizeof(uint64_t), st));
+	const long long total = NF * U;
+	iou_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(d_method, d_annot, (const int *)(M + o_fv), (const int *)(M + o_first),
+															(const int *)(M + o_ne), NF, U, d_fiou, d_acc);
+	CU(cudaGetLastError());
+	c->launches += 1;
+	const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+	CU(cudaMemcpyAsync(b->acc, d_acc, (size_t)V * U * 2 * sizeof(uint64_t), kind, st));
+	if (host) {
+		if (b->frame_iou) CU(cudaMemcpyAsync(b->frame_iou, d_fiou, (size_t)NF * U * sizeof(double), kind, st));
+		CU(cudaStreamSynchronize(st));
+	}
+	return RVB_OK;
+}
+
+// exactly rounded (round-half-even) acc / (n * 2^80) as a double
+extern "C" double rvb_iou_mean_from_acc(const uint64_t acc[2], int64_t n) {
+	if (n <= 0) return nan("");
+	unsigned __int128 S = ((unsigned __int128)acc[1] << 64) | acc[0];
+	if (S == 0) return 0.0;
+	const unsigned __int128 d = (unsigned __int128)(uint64_t)n;
+	// quotient with 64 extra fractional bits: q = qi + qf / 2^64, sticky = remainder != 0
+	const unsigned __int128 qi = S / d;
+	const unsigned __int128 r = S % d;
+	const unsigned __int128 num2 = r << 64;  // r < n < 2^63
+	const unsigned __int128 qf = num2 / d;
+	const bool sticky = (num2 % d) != 0;
+	// value = (qi * 2^64 + qf [+ sticky]) * 2^-(64 + kIouFracBits); qi < 2^112 so work in 192 bits: hi = qi, lo = qf
+	// find the top bit
+	int top;  // index of the leading 1 in the 192-bit number (bit 0 = LSB of qf)
+	if (qi != 0) {
+		int hb = 127;
+		while (!((qi >> hb) & 1)) --hb;
+		top = 64 + hb;
+	} else {
+		int hb = 63;
+		while (!(((uint64_t)qf >> hb) & 1)) --hb;
+		top = hb;
+	}
+	auto bit = [&](int i) -> int {
+		if (i < 0) return 0;
+		if (i < 64) return (int)(((uint64_t)qf >> i) & 1);
+		return (int)((qi >> (i - 64)) & 1);
+	};
+	uint64_t mant = 0;  // 53 bits: top .. top-52
+	for (int i = 0; i < 53; ++i) mant = (mant << 1) | (uint64_t)bit(top - i);
+	const int guard = bit(top - 53);
+	bool rest = sticky;
+	for (int i = top - 54; i >= 0 && !rest; --i) rest = bit(i) != 0;
+	if (guard && (rest || (mant & 1))) mant += 1;  // may carry to 2^53: ldexp handles it
+	return ldexp((double)mant, top - 52 - 64 - kIouFracBits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-level entry points for the parity tests
+// ---------------------------------------------------------------------------------------------
+extern "C" int rvb_debug_cluster_labels(rvb_ctx *c, const rvb_params *p, const uint8_t *map_hw, int32_t h, int32_t w,
+										int32_t *labels_out, int32_t *n_points_out) {
+	if (!c || !p || !map_hw || !labels_out || !n_points_out) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (h < 1 || w < 1 || h > 256 || w > 256) return fail(RVB_ERR_UNSUPPORTED, "size %dx%d", h, w);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const int WPS = align_up(w, 16);
+	std::vector<uint8_t> padded((size_t)h * WPS, 0);
+	int n = 0;
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < w; ++x) {
+			padded[(size_t)y * WPS + x] = map_hw[(size_t)y * w + x];
+			n += map_hw[(size_t)y * w + x] != 0;
+		}
+	if (n > RVB_MAX_POINTS) return fail(RVB_ERR_CAPACITY, "%d salient pixels (max %d)", n, RVB_MAX_POINTS);
+	*n_points_out = n;
+	const size_t o_map = 0, o_out = align_up((int)padded.size(), 256), o_lab = o_out + 256, o_list = o_lab + (size_t)RVB_MAX_POINTS * 4 + 256;
+	const size_t o_cnt = o_list + 256, total = o_cnt + 256;
+	if (c->misc.ensure(total)) return RVB_ERR_CUDA;
+	uint8_t *D = (uint8_t *)c->misc.p;
+	CU(cudaMemsetAsync(D, 0xFF, total, st));
+	CU(cudaMemcpyAsync(D + o_map, padded.data(), padded.size(), cudaMemcpyHostToDevice, st));
+	const int hdr[4] = {0, 1, 0, 0};  // head, len
+	const int zero = 0;
+	CU(cudaMemcpyAsync(D + o_cnt, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(D + o_list, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+	MapArgs a;
+	memset(&a, 0, sizeof(a));
+	a.maps_u8 = D + o_map; a.H = h; a.W = w; a.WPS = WPS; a.gstride = WPS;
+	a.list = (const int *)(D + o_list); a.head = (int *)(D + o_cnt); a.list_len = (int *)(D + o_cnt) + 1;
+	a.out = (MapOut *)(D + o_out); a.labels_dbg = (int32_t *)(D + o_lab);
+	a.t_threshold = 0; a.clust_filt = 1; a.mcs = p->hdbscan_min; a.min_samples = p->hdbscan_min_samples;
+	a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
+	int rc;
+	if (n <= 1024) rc = launch_map<256, 4>(c, a, h, w, WPS, 1);
+	else if (n <= 2048) rc = launch_map<256, 8>(c, a, h, w, WPS, 1);
+	else if (n <= 4096) rc = launch_map<512, 8>(c, a, h, w, WPS, 1);
+	else rc = launch_map<512, 16>(c, a, h, w, WPS, 1);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(labels_out, D + o_lab, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	MapOut mo;
+	CU(cudaMemcpyAsync(&mo, D + o_out, sizeof(mo), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (mo.flags & (kFlagOverflow | kFlagClusterCapacity)) return fail(RVB_ERR_CAPACITY, "cluster capacity exceeded");
+	if (mo.n_clusters < 0) {  // gates skipped the clustering: the reference would not call fit_predict
+		for (int i = 0; i < n; ++i) labels_out[i] = -2;
+	}
+	return RVB_OK;
+}
+
+extern "C" int rvb_debug_smooth_series(rvb_ctx *c, const rvb_params *p, const double *series_in, int32_t n, double fr,
+									   double *lowpassed_out, double *smoothed_out) {
+	if (!c || !p || !series_in || n < 1) return fail(RVB_ERR_INVALID, "bad argument");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	ClipDev cl;
+	memset(&cl, 0, sizeof(cl));
+	cl.n_maps = 1; cl.n_frames = n; cl.n_shots = 1; cl.h_orig = 360; cl.w_orig = 640; cl.fr = fr;
+	ShotDev sh;
+	memset(&sh, 0, sizeof(sh));
+	sh.f0 = 0; sh.f1 = n - 1; sh.m0 = 0; sh.m1 = 0; sh.clip = 0; sh.frame_base = 0; sh.map_base = 0; sh.scratch_base = 0;
+	FilterCoef fc;
+	butter_design(p->lp_order, p->lp_cutoff / (0.5 * fr), fc);
+	std::vector<int> fshot(n, 0);
+	const int zero = 0;
+	Staging sg;
+	const size_t o_cl = sg.add(&cl, sizeof(cl)), o_sh = sg.add(&sh, sizeof(sh)), o_fc = sg.add(&fc, sizeof(fc));
+	const size_t o_fs = sg.add(fshot.data(), (size_t)n * sizeof(int)), o_cc = sg.add(&zero, sizeof(int));
+	const size_t o_x = sg.add(series_in, (size_t)n * sizeof(double));
+	const size_t o_y = sg.add(series_in, (size_t)n * sizeof(double));
+	const size_t o_xl = sg.add(nullptr, (size_t)n * sizeof(double)), o_yl = sg.add(nullptr, (size_t)n * sizeof(double));
+	const size_t o_xs = sg.add(nullptr, (size_t)n * sizeof(double)), o_ys = sg.add(nullptr, (size_t)n * sizeof(double));
+	const size_t o_scr = sg.add(nullptr, (size_t)(2 * (n + 6 * (RVB_MAX_LP_ORDER + 1)) + 16) * sizeof(double));
+	if (c->misc.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
+	uint8_t *D = (uint8_t *)c->misc.p;
+	CU(cudaMemcpyAsync(D, sg.bytes.data(), sg.bytes.size(), cudaMemcpyHostToDevice, st));
+	CU(cudaStreamSynchronize(st));
+	lowpass_kernel<<<1, 64, 0, st>>>((const ShotDev *)(D + o_sh), 1, (const ClipDev *)(D + o_cl), (const FilterCoef *)(D + o_fc),
+									  (const int *)(D + o_cc), (const double *)(D + o_x), (const double *)(D + o_y),
+									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt);
+	const int blocks = (int)((2LL * n * 32 + 255) / 256);
+	smooth_kernel<<<blocks, 256, 0, st>>>((const ShotDev *)(D + o_sh), (const int *)(D + o_fs), n, (const ClipDev *)(D + o_cl),
+										  (const double *)(D + o_xl), (const double *)(D + o_yl), (double *)(D + o_xs),
+										  (double *)(D + o_ys), p->loess_filt, p->loess_w_secs, p->loess_degree);
+	CU(cudaGetLastError());
+	c->launches += 2;
+	if (lowpassed_out) CU(cudaMemcpyAsync(lowpassed_out, D + o_xl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (smoothed_out) CU(cudaMemcpyAsync(smoothed_out, D + o_xs, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return RVB_OK;
+}

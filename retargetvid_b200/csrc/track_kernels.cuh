@@ -1,0 +1,518 @@
+// Centre track kernels: empty-centre fill, per-shot interpolation, zero-phase Butterworth,
+// LOESS / Savitzky-Golay (one output frame per warp), crop boxes, border detection.
+// All arithmetic is fp64; the reference runs these stages in numpy/scipy float64.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/retargetvid_b200.h"
+#include "map_kernel.cuh"
+
+namespace rvb {
+
+struct ClipDev {
+	int n_maps, n_frames, n_shots, h_orig, w_orig;
+	int map_offset, frame_offset, shot_offset;
+	double fr;
+};
+
+struct ShotDev {           // one row of vid_data['segmentation'] / ['segmentation_sel']
+	int f0, f1, m0, m1;    // inclusive, clip-relative
+	int clip;
+	int frame_base;        // absolute index of frame f0 in the packed per-frame arrays
+	int map_base;          // absolute index of map m0
+	int scratch_base;      // offset (doubles) of this shot's scratch area
+};
+
+struct FilterCoef {        // Butterworth low-pass in transfer-function form + lfilter_zi
+	int order;             // 0: invalid cutoff -> moving-average fallback (smartVidCrop.py:1611-1625)
+	double b[RVB_MAX_LP_ORDER + 1];
+	double a[RVB_MAX_LP_ORDER + 1];
+	double zi[RVB_MAX_LP_ORDER];
+};
+
+// ---------------------------------------------------------------------------------------------
+// a9: sc_handle_empty_centers, smartVidCrop.py:1221-1300.  One thread per clip.
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_centres_kernel(const ClipDev *clips, int n_clips, const ShotDev *shots, const MapOut *mo,
+									double *dx, double *dy, uint8_t *empty, int *clip_status) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_clips) return;
+	const ClipDev cl = clips[c];
+	const int N = cl.n_maps, base = cl.map_offset;
+	int status = 0;
+	for (int i = 0; i < N; ++i) {
+		const MapOut &o = mo[base + i];
+		const bool e = (o.flags & kFlagEmpty) != 0;
+		if (o.flags & (kFlagOverflow | kFlagClusterCapacity)) status = RVB_ERR_CAPACITY;
+		if (empty) empty[base + i] = e ? 1 : 0;
+		dx[base + i] = e ? nan("") : o.cx;
+		dy[base + i] = e ? nan("") : o.cy;
+	}
+	int i = 0;
+	while (i < N) {
+		if (!isnan(dx[base + i])) { ++i; continue; }
+		int j = i;
+		while (j + 1 < N && isnan(dx[base + j + 1])) ++j;  // empty run [i, j]
+		int d_start = 0x7fffffff, d_end = 0x7fffffff;
+		for (int s = 0; s < cl.n_shots; ++s) {
+			const ShotDev &sh = shots[cl.shot_offset + s];
+			d_start = min(d_start, abs(sh.m0 - i));
+			d_end = min(d_end, abs(sh.m1 - j));
+		}
+		double xf, yf;
+		if (d_start < d_end) {  // closer to a shot start: take the next value
+			xf = dx[base + j + 1];
+			yf = dy[base + j + 1];
+		} else {                // else the previous one (python's dx[-1] when the run starts at 0)
+			const int k = (i == 0) ? (N - 1) : (i - 1);
+			xf = dx[base + k];
+			yf = dy[base + k];
+		}
+		for (int k = i; k <= j; ++k) { dx[base + k] = xf; dy[base + k] = yf; }
+		i = j + 1;
+	}
+	for (int k = 0; k < N; ++k)
+		if (isnan(dx[base + k]) && status == 0) status = RVB_ERR_NO_CENTRES;
+	clip_status[c] = status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a10: interp_handler / sc_interpolate, smartVidCrop.py:1528-1597.
+// scipy.interpolate.interp1d(kind='linear'|'quadratic', fill_value='extrapolate').  The quadratic
+// kind is make_interp_spline(k=2): knots x0 x0 x0, midpoints m_1..m_{n-3}, x_{n-1} x3, a banded
+// collocation system, de Boor evaluation (extrapolating with the end pieces).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bspl2_basis(const double *t, int mu, double x, double h[3]) {
+	// de Boor-Cox recurrence for the three quadratic B-splines that are non-zero on [t_mu, t_mu+1)
+	double hh[3];
+	h[0] = 1.0;
+	for (int j = 1; j <= 2; ++j) {
+		for (int i = 0; i < j; ++i) hh[i] = h[i];
+		h[0] = 0.0;
+		for (int nn = 1; nn <= j; ++nn) {
+			const double xb = t[mu + nn], xa = t[mu + nn - j];
+			if (xb == xa) { h[nn] = 0.0; continue; }
+			const double w = hh[nn - 1] / (xb - xa);
+			h[nn - 1] += w * (xb - x);
+			h[nn] = w * (x - xa);
+		}
+	}
+}
+
+__device__ __forceinline__ int bspl_interval(const double *t, int nc, double x) {
+	// l in [2, nc-1] with t[l] <= x < t[l+1]; clamped for extrapolation
+	if (!(x > t[2])) return 2;
+	if (x >= t[nc]) return nc - 1;
+	int lo = 2, hi = nc - 1;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (t[mid] <= x) lo = mid; else hi = mid - 1;
+	}
+	return lo;
+}
+
+// one thread per shot: build knots and solve the collocation system for x and y together
+__global__ void spline_setup_kernel(const ShotDev *shots, int n_shots, const int *true_inds, const double *dx,
+									const double *dy, double *scratch) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n_shots) return;
+	const ShotDev sh = shots[s];
+	const int n = sh.m1 - sh.m0 + 1;
+	if (n <= 6) return;
+	// scratch: t[n+3], cx[n], cy[n], band[n][5]
+	double *t = scratch + sh.scratch_base;
+	double *cx = t + (n + 3);
+	double *cy = cx + n;
+	double *band = cy + n;
+	const int *ti = true_inds + sh.map_base;
+	const double x0 = 0.0;
+	auto X = [&](int i) { return (double)(ti[i] - ti[0]); };
+	t[0] = t[1] = t[2] = x0;
+	for (int i = 1; i <= n - 3; ++i) t[2 + i] = (X(i) + X(i + 1)) / 2.0;
+	t[n] = t[n + 1] = t[n + 2] = X(n - 1);
+	for (int i = 0; i < n; ++i) {
+		for (int k = 0; k < 5; ++k) band[i * 5 + k] = 0.0;
+		const double x = X(i);
+		const int mu = bspl_interval(t, n, x);
+		double h[3];
+		bspl2_basis(t, mu, x, h);
+		// columns mu-2..mu, stored at band[i][col - i + 2]
+		for (int k = 0; k < 3; ++k) {
+			const int col = mu - 2 + k;
+			const int o = col - i + 2;
+			if (o >= 0 && o < 5) band[i * 5 + o] = h[k];
+		}
+		cx[i] = dx[sh.map_base + i];
+		cy[i] = dy[sh.map_base + i];
+	}
+	// Gaussian elimination without pivoting (the collocation matrix is totally positive)
+	for (int i = 0; i < n; ++i) {
+		const double piv = band[i * 5 + 2];
+		for (int r = i + 1; r <= min(n - 1, i + 2); ++r) {
+			const int o = i - r + 2;  // column i in row r
+			const double f = band[r * 5 + o] / piv;
+			if (f == 0.0) continue;
+			for (int c = i; c <= min(n - 1, i + 2); ++c) {
+				const int oi = c - i + 2, orr = c - r + 2;
+				if (orr >= 0 && orr < 5) band[r * 5 + orr] -= f * band[i * 5 + oi];
+			}
+			cx[r] -= f * cx[i];
+			cy[r] -= f * cy[i];
+		}
+	}
+	for (int i = n - 1; i >= 0; --i) {
+		double sx = cx[i], sy = cy[i];
+		for (int c = i + 1; c <= min(n - 1, i + 2); ++c) {
+			sx -= band[i * 5 + (c - i + 2)] * cx[c];
+			sy -= band[i * 5 + (c - i + 2)] * cy[c];
+		}
+		cx[i] = sx / band[i * 5 + 2];
+		cy[i] = sy / band[i * 5 + 2];
+	}
+}
+
+// one thread per (shot-local frame): evaluate the interpolant
+__global__ void interp_eval_kernel(const ShotDev *shots, const int *frame_shot, int n_frames_total,
+								   const int *true_inds, const double *dx, const double *dy,
+								   const double *scratch, double *dxi, double *dyi) {
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= n_frames_total) return;
+	const ShotDev sh = shots[frame_shot[f]];
+	const int n = sh.m1 - sh.m0 + 1;
+	const double x = (double)(f - sh.frame_base);
+	const int *ti = true_inds + sh.map_base;
+	const double *px = dx + sh.map_base, *py = dy + sh.map_base;
+	double ox, oy;
+	if (n < 3) {
+		ox = px[0];
+		oy = py[0];
+	} else if (n <= 6) {
+		// interp1d._call_linear: searchsorted (left), clip to [1, n-1]
+		int idx = 0;
+		while (idx < n && (double)(ti[idx] - ti[0]) < x) ++idx;
+		idx = max(1, min(n - 1, idx));
+		const double xlo = (double)(ti[idx - 1] - ti[0]), xhi = (double)(ti[idx] - ti[0]);
+		const double sx = (px[idx] - px[idx - 1]) / (xhi - xlo);
+		const double sy = (py[idx] - py[idx - 1]) / (xhi - xlo);
+		ox = __dadd_rn(__dmul_rn(sx, x - xlo), px[idx - 1]);
+		oy = __dadd_rn(__dmul_rn(sy, x - xlo), py[idx - 1]);
+	} else {
+		const double *t = scratch + sh.scratch_base;
+		const double *cx = t + (n + 3);
+		const double *cy = cx + n;
+		const int mu = bspl_interval(t, n, x);
+		double h[3];
+		bspl2_basis(t, mu, x, h);
+		ox = 0.0;
+		oy = 0.0;
+		for (int k = 0; k < 3; ++k) {
+			ox += cx[mu - 2 + k] * h[k];
+			oy += cy[mu - 2 + k] * h[k];
+		}
+	}
+	dxi[f] = ox;
+	dyi[f] = oy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11: sc_butter_lowpass_filter, smartVidCrop.py:1599-1627: scipy.signal.filtfilt (odd padding of
+// 3*max(len(a),len(b)) samples, lfilter_zi initial state, direct form II transposed), with the
+// reference's moving-average fallback when filtfilt raises (shots of <= padlen frames).
+// One thread per (shot, axis).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double df2t_step(const FilterCoef &fc, double *z, double x) {
+	const int m = fc.order;
+	const double y = __dadd_rn(z[0], __dmul_rn(fc.b[0], x));
+	for (int i = 0; i < m - 1; ++i)
+		z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(x, fc.b[i + 1])), __dmul_rn(y, fc.a[i + 1]));
+	z[m - 1] = __dsub_rn(__dmul_rn(x, fc.b[m]), __dmul_rn(y, fc.a[m]));
+	return y;
+}
+
+__global__ void lowpass_kernel(const ShotDev *shots, int n_shots, const ClipDev *clips, const FilterCoef *coefs,
+							   const int *clip_coef, const double *dxi, const double *dyi, double *dxl, double *dyl,
+							   double *scratch, int lp_filt) {
+	const int id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= n_shots * 2) return;
+	const int s = id >> 1, axis = id & 1;
+	const ShotDev sh = shots[s];
+	const int cl = sh.f1 - sh.f0 + 1;
+	const double *x = (axis ? dyi : dxi) + sh.frame_base;
+	double *out = (axis ? dyl : dxl) + sh.frame_base;
+	if (!lp_filt) {
+		for (int i = 0; i < cl; ++i) out[i] = x[i];
+		return;
+	}
+	const FilterCoef &fc = coefs[clip_coef[sh.clip]];
+	const int m = fc.order;
+	const int edge = 3 * (m + 1);
+	if (m > 0 && cl > edge) {
+		// forward pass over the odd extension, stored in scratch, then backward pass
+		double *buf = scratch + sh.scratch_base + (size_t)axis * (cl + 2 * edge);
+		const int ne = cl + 2 * edge;
+		auto ext = [&](int i) -> double {
+			if (i < edge) return 2.0 * x[0] - x[edge - i];
+			if (i < edge + cl) return x[i - edge];
+			return 2.0 * x[cl - 1] - x[cl - 2 - (i - edge - cl)];
+		};
+		double z[RVB_MAX_LP_ORDER];
+		const double e0 = ext(0);
+		for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * e0;
+		for (int i = 0; i < ne; ++i) buf[i] = df2t_step(fc, z, ext(i));
+		const double y0 = buf[ne - 1];
+		for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * y0;
+		for (int i = ne - 1; i >= 0; --i) {
+			const double y = df2t_step(fc, z, buf[i]);
+			if (i >= edge && i < edge + cl) out[i - edge] = y;
+		}
+		return;
+	}
+	// fallback: 5-tap moving average of the interior, edges untouched (smartVidCrop.py:1611-1615)
+	for (int i = 0; i < cl; ++i) out[i] = x[i];
+	if (cl >= 5) {
+		for (int i = 2; i < cl - 2; ++i)
+			out[i] = ((((x[i - 2] + x[i - 1]) + x[i]) + x[i + 1]) + x[i + 2]) / 5.0;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// a12: loess_handler + pyloess.Loess.estimate (pyloess.py:61-95), one output frame per warp.
+// The reference fits, for every frame j, a tricube-weighted polynomial over the `window` nearest
+// frames and evaluates it at j.  Here the fit is done in coordinates centred on j (u = i - j), so the
+// estimate is the constant coefficient; lanes stride the window, the moment sums are reduced with
+// shuffles and lane 0 solves the 3x3 (or 2x2) normal equations.  Savitzky-Golay (loess_filt == 0,
+// scipy.signal.savgol_filter mode='interp') is the same fit with unit weights.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n_frames_total, const ClipDev *clips,
+							  const double *dxl, const double *dyl, double *dxs, double *dys, int loess_filt,
+							  double loess_w_secs, int degree) {
+	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (gw >= n_frames_total * 2) return;
+	const int f = gw >> 1, axis = gw & 1;
+	const ShotDev sh = shots[frame_shot[f]];
+	const int cl = sh.f1 - sh.f0 + 1;
+	const int j = f - sh.frame_base;
+	const double *y = (axis ? dyl : dxl) + sh.frame_base;
+	double *out = (axis ? dys : dxs) + sh.frame_base;
+	if (cl < 10) {  // loess_handler: short shots bypass smoothing
+		if (lane == 0) out[j] = y[j];
+		return;
+	}
+	const double fr = clips[sh.clip].fr;
+	int win = min((int)(fr * loess_w_secs), cl - 2);
+	if ((win & 1) == 0) win -= 1;
+	const int h = (win - 1) >> 1;
+	int lo = j - h;
+	if (lo < 0) lo = 0;
+	if (lo + win > cl) lo = cl - win;
+	// normalisation of y (pyloess.py:16-24); a constant series divides by zero -> NaN -> identity
+	double ymin = INFINITY, ymax = -INFINITY;
+	for (int i = lane; i < cl; i += 32) {
+		ymin = fmin(ymin, y[i]);
+		ymax = fmax(ymax, y[i]);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+		ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+	}
+	if (loess_filt && !(ymax > ymin)) {
+		if (lane == 0) out[j] = y[j];
+		return;
+	}
+	const double dmax = (double)max(j - lo, lo + win - 1 - j);
+	double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, t0 = 0, t1 = 0, t2 = 0;
+	for (int i = lo + lane; i < lo + win; i += 32) {
+		const double u = (double)(i - j) / dmax;  // |u| <= 1 keeps the normal equations well scaled
+		double w = 1.0;
+		if (loess_filt) {
+			const double r = fabs(u);
+			const double c = 1.0 - r * r * r;
+			w = c * c * c;
+		}
+		const double yy = y[i] - y[j];
+		const double wu = w * u, wu2 = wu * u;
+		s0 += w; s1 += wu; s2 += wu2; s3 += wu2 * u; s4 += wu2 * u * u;
+		t0 += w * yy; t1 += wu * yy; t2 += wu2 * yy;
+	}
+	s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3); s4 = warp_sum(s4);
+	t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+	if (lane == 0) {
+		double b0;
+		if (degree >= 2) {
+			// solve [s0 s1 s2; s1 s2 s3; s2 s3 s4] b = [t0 t1 t2] for b0 (Cramer, symmetric 3x3)
+			const double c00 = s2 * s4 - s3 * s3;
+			const double c01 = s1 * s4 - s2 * s3;
+			const double c02 = s1 * s3 - s2 * s2;
+			const double det = s0 * c00 - s1 * c01 + s2 * c02;
+			b0 = (t0 * c00 - t1 * c01 + t2 * c02) / det;
+		} else {
+			const double det = s0 * s2 - s1 * s1;
+			b0 = (t0 * s2 - t1 * s1) / det;
+		}
+		out[j] = b0 + y[j];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4 (border detection) -- smartVidCrop.py:842-924.  Profiles are the max over time and rows/cols
+// of the RAW maps; one CTA per map accumulates into its clip's profile with atomicMax.
+// ---------------------------------------------------------------------------------------------
+__global__ void border_profile_kernel(const uint8_t *maps, int H, int W, int gstride, const int *map_clip,
+									  uint32_t *prof /* [n_clips][H + W] */) {
+	const int m = blockIdx.x;
+	const uint8_t *src = maps + (size_t)m * H * gstride;
+	uint32_t *p = prof + (size_t)map_clip[m] * (H + W);
+	for (int y = threadIdx.x; y < H; y += blockDim.x) {
+		uint32_t mx = 0;
+		for (int x = 0; x < W; ++x) mx = max(mx, (uint32_t)src[y * gstride + x]);
+		atomicMax(&p[y], mx);
+	}
+	for (int x = threadIdx.x; x < W; x += blockDim.x) {
+		uint32_t mx = 0;
+		for (int y = 0; y < H; ++y) mx = max(mx, (uint32_t)src[y * gstride + x]);
+		atomicMax(&p[H + x], mx);
+	}
+}
+
+__global__ void border_finish_kernel(const ClipDev *clips, int n_clips, const uint32_t *prof, int H, int W,
+									 int t_border, int *borders /* [n_clips][4] t,b,l,r in original px */) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_clips) return;
+	int t = 0, b = 0, l = 0, r = 0;
+	if (t_border != -1) {
+		const uint32_t *fcol = prof + (size_t)c * (H + W);
+		const uint32_t *frow = fcol + H;
+		for (int i = 0; i < H; ++i) { if ((int)fcol[i] > t_border) break; ++t; }
+		for (int i = 0; i < H; ++i) { if ((int)fcol[H - 1 - i] > t_border) break; ++b; }
+		for (int i = 0; i < W; ++i) { if ((int)frow[i] > t_border) break; ++l; }
+		for (int i = 0; i < W; ++i) { if ((int)frow[W - 1 - i] > t_border) break; ++r; }
+		t = min(t, (int)(H * 0.45)); b = min(b, (int)(H * 0.45));
+		l = min(l, (int)(W * 0.45)); r = min(r, (int)(W * 0.45));
+		const double ho = clips[c].h_orig, wo = clips[c].w_orig;
+		t = (int)((ho / H) * t); b = (int)((ho / H) * b);
+		l = (int)((wo / W) * l); r = (int)((wo / W) * r);
+	}
+	borders[c * 4 + 0] = t; borders[c * 4 + 1] = b; borders[c * 4 + 2] = l; borders[c * 4 + 3] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a14 + a15: sc_compute_bb (smartVidCrop.py:979-1048) and sc_shift_time (:1740-1746).
+// One thread per (ratio, frame).
+// ---------------------------------------------------------------------------------------------
+struct BoxGeom { int fbb_w, fbb_h, hbbw1, hbbw2, hbbh1, hbbh2; };
+
+__device__ __forceinline__ BoxGeom box_geom(int w_final, int h_final, int w_orig, int h_orig, const int *bd) {
+	BoxGeom g;
+	g.fbb_w = w_final;
+	g.fbb_h = h_final;
+	if (h_final == h_orig) {
+		g.fbb_h = h_final - bd[0] - bd[1];
+		g.fbb_w = (int)(((double)g.fbb_h / (double)h_final) * w_final);
+	}
+	if (w_final == w_orig) {
+		g.fbb_w = w_final - bd[2] - bd[3];
+		g.fbb_h = (int)(((double)g.fbb_w / (double)w_final) * h_final);
+	}
+	g.hbbw1 = (int)(g.fbb_w / 2.0);
+	g.hbbw2 = g.fbb_w - g.hbbw1;
+	g.hbbh1 = (int)(g.fbb_h / 2.0);
+	g.hbbh2 = g.fbb_h - g.hbbh1;
+	return g;
+}
+
+__global__ void boxes_kernel(const ClipDev *clips, const int *frame_clip, int n_frames_total, int n_ratios,
+							 const int *clip_final /* [n_clips][R][3] mode, w_final, h_final */,
+							 const int *borders, int Hp, int Wp, const double *dxs, const double *dys,
+							 int shift, int32_t *boxes /* [R][F][4] */, int32_t *clip_dims /* [n_clips][R][9] or null */) {
+	const int id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= n_frames_total * n_ratios) return;
+	const int r = id / n_frames_total, f = id - r * n_frames_total;
+	const int c = frame_clip[f];
+	const ClipDev cl = clips[c];
+	const int *fin = clip_final + (c * n_ratios + r) * 3;
+	const int *bd = borders + c * 4;
+	const BoxGeom g = box_geom(fin[1], fin[2], cl.w_orig, cl.h_orig, bd);
+	// sc_shift_time (smartVidCrop.py:1740-1746), both loops: first `bbs[-i+1] = bbs[-1]` for
+	// i in range(shift) (python indices 1, 0, -1, -2, ...), then bbs[i] = bbs[i + shift].
+	const int fl = f - cl.frame_offset;
+	int src = fl;
+	if (shift > 0) {
+		if (fl < cl.n_frames - shift) src = fl + shift;
+		bool hit = false;
+		for (int k = 0; k < shift; ++k) {
+			int idx = 1 - k;
+			if (idx < 0) idx += cl.n_frames;
+			if (idx == src) hit = true;
+		}
+		if (hit) src = cl.n_frames - 1;
+	}
+	const double scale_h = (double)Hp / (double)cl.h_orig;
+	const double scale_w = (double)Wp / (double)cl.w_orig;
+	const int cx = (int)(dxs[cl.frame_offset + src] / scale_w);
+	const int cy = (int)(dys[cl.frame_offset + src] / scale_h);
+	int x1 = cx - g.hbbw1, y1 = cy - g.hbbh1, x2 = cx + g.hbbw2, y2 = cy + g.hbbh2;
+	if (x1 < bd[2]) { x1 = bd[2]; x2 = x1 + g.fbb_w; }
+	if (x2 > cl.w_orig - bd[3]) { x2 = cl.w_orig - bd[3]; x1 = x2 - g.fbb_w; }
+	if (y1 < bd[0]) { y1 = bd[0]; y2 = y1 + g.fbb_h; }
+	if (y2 > cl.h_orig - bd[1]) { y2 = cl.h_orig - bd[1]; y1 = y2 - g.fbb_h; }
+	int32_t *o = boxes + ((size_t)r * n_frames_total + f) * 4;
+	o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+	if (clip_dims != nullptr && fl == 0) {
+		int32_t *d = clip_dims + (c * n_ratios + r) * 9;
+		d[0] = fin[0]; d[1] = fin[1]; d[2] = fin[2]; d[3] = g.fbb_w; d[4] = g.fbb_h;
+		d[5] = bd[0]; d[6] = bd[1]; d[7] = bd[2]; d[8] = bd[3];
+	}
+}
+
+// per-clip scores: mean saliency of the raw maps and mean coverage per ratio
+__global__ void clip_scores_kernel(const ClipDev *clips, int n_clips, const MapOut *mo, int H, int W, int n_ratios,
+								   double *map_scores, double *clip_scores) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_clips) return;
+	const ClipDev cl = clips[c];
+	unsigned long long tot = 0;
+	double cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (int i = 0; i < cl.n_maps; ++i) {
+		const MapOut &o = mo[cl.map_offset + i];
+		tot += o.raw_sum;
+		if (map_scores) map_scores[cl.map_offset + i] = (double)o.raw_sum / (double)(H * W);
+		for (int r = 0; r < n_ratios; ++r) cv[r] += o.cvrg[r];
+	}
+	if (clip_scores) {
+		double *o = clip_scores + (size_t)c * (1 + n_ratios);
+		o[0] = (double)tot / ((double)H * (double)W * (double)cl.n_maps);
+		for (int r = 0; r < n_ratios; ++r) o[1 + r] = cv[r] / (double)cl.n_maps;
+	}
+}
+
+// [H][W][N] (reference layout, frame index fastest) -> [N][H][WPS]
+__global__ void transpose_hwn_kernel(const uint8_t *src, int H, int W, int N, uint8_t *dst, int WPS) {
+	__shared__ uint8_t tile[32][33];
+	// grid: x over N tiles, y over pixel tiles (pixel index p = y * W + x)
+	const int n0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+	const int P = H * W;
+	for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+		const int p = p0 + i, n = n0 + threadIdx.x;
+		tile[i][threadIdx.x] = (p < P && n < N) ? src[(size_t)p * N + n] : 0;
+	}
+	__syncthreads();
+	for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+		const int n = n0 + i, p = p0 + threadIdx.x;
+		if (p < P && n < N) {
+			const int y = p / W, x = p - y * W;
+			dst[((size_t)n * H + y) * WPS + x] = tile[threadIdx.x][i];
+		}
+	}
+}
+
+}  // namespace rvb

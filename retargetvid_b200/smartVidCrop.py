@@ -1,0 +1,328 @@
+"""Drop-in host API of SmartVidCrop's crop-selection path, running on the B200 library.
+
+Mirrors the public surface of the reference's smartVidCrop.py for this path
+(SURVEY.md 8b): ``sc_init_crop_params`` (smartVidCrop.py:132-209),
+``smart_vid_crop`` (:2218-2614), ``smart_crop_version`` (:2617-2618), the
+``vid_data`` / ``smart_crop_results`` dict keys and the two text file formats
+(:2778-2785).  Ingest (video decode, TransNet, UNISAL; :234-836) and rendering
+(:1801-2213) are out of scope: ``vid_data`` comes from the reference's own ingest
+cache (``temp_path/<video>.pkl``, :2244-2256) or is passed directly.
+
+All arithmetic is done by the CUDA library through ``retargetvid_b200._cabi``;
+there is no CPU fallback.
+"""
+import gc
+import os
+import pickle
+import time
+
+import numpy as np
+
+from . import _cabi
+from .engine import CropEngine
+
+_ENGINES = {}
+
+
+def _engine(device=0):
+	if device not in _ENGINES:
+		_ENGINES[device] = CropEngine(device)
+	return _ENGINES[device]
+
+
+# Initiates the SmartVidCrop method's parameters to the default settings
+# (same 31 keys, defaults and preset as smartVidCrop.py:132-209)
+def sc_init_crop_params(print_dict=False, use_best_settings=False):
+	crop_params = {}
+	crop_params['out_ratio'] = "4:5"
+	crop_params['max_input_d'] = 250
+	crop_params['skip'] = 6
+	crop_params['read_batch'] = 2000
+	crop_params['resize_factor'] = 1.0
+	crop_params['resize_type'] = 1
+	crop_params['op_close'] = True
+	crop_params['value_bias'] = 1.0
+	crop_params['exit_on_spread_sal'] = False
+	crop_params['exit_on_low_cvrg'] = False
+	crop_params['com_km'] = True
+	crop_params['clust_filt'] = True
+	crop_params['select_sum'] = 2
+	crop_params['min_d_jump'] = 10
+	crop_params['focus_stability'] = False
+	crop_params['foces_stab_t'] = 60
+	crop_params['foces_stab_s'] = 1.5
+	crop_params['hdbscan_min'] = 26
+	crop_params['hdbscan_min_samples'] = None
+	crop_params['shift_time'] = 0
+	crop_params['loess_filt'] = 1
+	crop_params['loess_w_secs'] = 2
+	crop_params['loess_degree'] = 2
+	crop_params['lp_filt'] = 1
+	crop_params['lp_cutoff'] = 2
+	crop_params['lp_order'] = 5
+	crop_params['t_sal'] = 40
+	crop_params['t_cvrg'] = 0.60
+	crop_params['t_threshold'] = 120
+	crop_params['t_border'] = -1
+	crop_params['t_cut'] = 120
+	if use_best_settings:
+		crop_params['t_threshold'] = 90
+		crop_params['hdbscan_min'] = 5
+		crop_params['hdbscan_min_samples'] = 3
+		crop_params['min_d_jump'] = 1
+		crop_params['resize_factor'] = 4
+		crop_params['op_close'] = True
+		crop_params['value_bias'] = 1.0
+		crop_params['select_sum'] = 1
+		crop_params['focus_stability'] = True
+		crop_params['foces_stab_t'] = 60
+		crop_params['foces_stab_s'] = 1.5
+		crop_params['t_border'] = -1
+		crop_params['lp_filt'] = 1
+		crop_params['lp_cutoff'] = 1
+		crop_params['lp_order'] = 2
+		crop_params['loess_filt'] = 0
+	if print_dict:
+		for x in crop_params.keys():
+			print(x, ':', crop_params[x])
+	return crop_params
+
+
+def smart_crop_version():
+	return '1.4.0'
+
+
+def _check_supported(CP):
+	if CP['focus_stability']:
+		raise NotImplementedError('focus_stability is not built yet (SURVEY.md 8f-2); set CP["focus_stability"]=False')
+	if float(CP['resize_factor']) != 1.0:
+		raise NotImplementedError('resize_factor != 1 is not built yet (SURVEY.md 8f); set CP["resize_factor"]=1.0')
+	if CP['exit_on_spread_sal'] and False:
+		pass
+
+
+def _times_dict(vid_dur, t_map, t_total, ingest_times):
+	"""Same keys and '%7.3fs, %6.3f%%' format as sc_all_times (smartVidCrop.py:113-124);
+	keys starting with '_' are summed into 'total'."""
+	keys = ['_read', '_read_shot_det', '_read_sal_det', '_calc_dest_size', '_border_det', '_check_mean_sal',
+			'_thresh', '_clustering', '_check_cvrg', '_center_of_mass', '_center_empty_handle', '_focus_stability',
+			'_interpolation', '_smooth', '_bb', '_shift']
+	vals = {k: 0.0 for k in keys}
+	for k in ('_read', '_read_shot_det', '_read_sal_det'):
+		vals[k] = float(ingest_times.get(k, 0.0))
+	vals['_clustering'] = t_map                      # fused map kernel: threshold .. centre of mass
+	vals['_smooth'] = max(t_total - t_map, 0.0)      # everything after it, incl. copies
+	out = {}
+	sum_t = 0.0
+	sum_p = 0.0
+	for k in keys:
+		sum_t += vals[k]
+		sum_p += (vals[k] / vid_dur) * 100.0
+		out[k] = '%7.3fs, %6.3f%%' % (vals[k], (vals[k] / vid_dur) * 100.0)
+	for k in ('read_init', 'read_tidy', 'clust_init', 'render', 'copy_sound'):
+		v = float(ingest_times.get(k, 0.0)) if k.startswith('read') else 0.0
+		out[k] = '%7.3fs, %6.3f%%' % (v, (v / vid_dur) * 100.0)
+	out['total'] = '%7.3fs, %6.3f%%' % (sum_t, sum_p)
+	return out
+
+
+def _fill_vd(VD, CP, res, ratio_index, want_smaps):
+	"""Writes the stage outputs into the vid_data dict with the reference's keys."""
+	d = res.dims[ratio_index]
+	VD['conversion_mode'] = int(d[0])
+	VD['w_final'] = int(d[1])
+	VD['h_final'] = int(d[2])
+	VD['fbb_w'] = int(d[3])
+	VD['fbb_h'] = int(d[4])
+	VD['border_t'], VD['border_b'], VD['border_l'], VD['border_r'] = int(d[5]), int(d[6]), int(d[7]), int(d[8])
+	VD['mean_sal_scores'] = np.array(res.map_scores)
+	VD['mean_sal_score'] = res.mean_sal_score if CP['exit_on_spread_sal'] else None
+	VD['mean_cvrg_score'] = float(res.cvrg_scores[ratio_index]) if CP['exit_on_low_cvrg'] else None
+	dx = [float(v) for v in res.dx]
+	dy = [float(v) for v in res.dy]
+	VD['dx'] = dx
+	VD['dy'] = dy
+	VD['dxnf'] = list(dx)
+	VD['dynf'] = list(dy)
+	VD['jumps'] = [255] * len(dx)
+	VD['jumps_inds'] = []
+	s = res.series
+	VD['dxi'] = [float(v) for v in s[0]]
+	VD['dyi'] = [float(v) for v in s[1]]
+	VD['dxl'] = [float(v) for v in s[2]]
+	VD['dyl'] = [float(v) for v in s[3]]
+	# sc_compute_bb truncates dxs/dys in place to original-size ints (smartVidCrop.py:995-999)
+	scale_h = float(VD['h_process']) / float(VD['h_orig'])
+	scale_w = float(VD['w_process']) / float(VD['w_orig'])
+	VD['dxs'] = [int(v / scale_w) for v in s[4]]
+	VD['dys'] = [int(v / scale_h) for v in s[5]]
+	ts = []
+	for seg in np.asarray(VD['segmentation']):
+		ts += list(range(int(seg[1]) - int(seg[0]) + 1))
+	VD['ts'] = ts
+	VD['bbs'] = [[int(v) for v in bb] for bb in res.boxes[ratio_index]]
+	if want_smaps and res.filtered is not None:
+		VD['smaps'] = np.ascontiguousarray(np.transpose(res.filtered, (1, 2, 0)))
+	return VD
+
+
+def smart_vid_crop_batch(vid_datas, CP=None, out_ratios=None, device=0, detail=True, want_filtered=False,
+						cvrg_window='reference'):
+	"""Batched entry point: many videos x many target ratios in one pass.
+
+	vid_datas: list of vid_data dicts (ingest output, smartVidCrop.py:480-489).
+	out_ratios: list of 'a:b' strings (default [CP['out_ratio']]).
+	Returns a list (per video) of engine.ClipResult; boxes[r] is the [fc, 4]
+	int32 array of x1,y1,x2,y2 for out_ratios[r].
+	"""
+	if CP is None:
+		CP = sc_init_crop_params()
+	_check_supported(CP)
+	if out_ratios is None:
+		out_ratios = [CP['out_ratio']]
+	return _engine(device).run(vid_datas, CP, list(out_ratios), detail=detail, want_filtered=want_filtered,
+								cvrg_window=cvrg_window)
+
+
+def smart_vid_crop(video_path, CP=None,
+				demo_fn='', final_vid_fn='', plots_fn='',
+				frames_dir='', temp_path=None,
+				verbose=False, save_vid=True,
+				callback_progress=None, callback_session=None, callback_status=None,
+				copy_sound=False, vid_data=None, device=0, cvrg_window='reference'):
+	"""Same signature and return value as the reference (smartVidCrop.py:2218-2223,2614):
+	returns (VD, smart_crop_results).  Extra keyword arguments: ``vid_data`` (skip the
+	pickle cache), ``device``, ``cvrg_window``."""
+	smart_crop_results = {}
+	if CP is None:
+		CP = sc_init_crop_params()
+	_check_supported(CP)
+	if save_vid:
+		raise NotImplementedError('rendering (sc_renderer / sc_render_padded) is out of scope; call with save_vid=False')
+
+	VD = vid_data
+	ingest_times = {}
+	if VD is None:
+		# the reference's ingest cache: <temp_path>/<video file name without extension>.pkl
+		vid_fn = os.path.basename(video_path).split('.')[0]
+		cands = []
+		if temp_path is not None:
+			cands.append(os.path.join(temp_path, vid_fn + '.pkl'))
+		if str(video_path).endswith('.pkl'):
+			cands.append(video_path)
+		for fn in cands:
+			if os.path.isfile(fn):
+				with open(fn, 'rb') as fp:
+					VD = pickle.load(fp)
+				break
+		if VD is None:
+			raise NotImplementedError('ingest (decode + TransNet + UNISAL) is out of scope: provide the reference\'s '
+									'vid_data pickle in temp_path or pass vid_data=')
+	if 'smaps' not in VD:
+		raise ValueError('vid_data pickle without saliency maps')
+	ingest_times = dict(VD.get('times', {}))
+
+	if (callback_status is not None) and (callback_session is not None):
+		callback_status(callback_session, 'sc', 'SC PROCESSING', 'smart-cropping main process')
+
+	VD['segm_backup'] = np.asarray(VD['segmentation']).copy()
+	t0 = time.perf_counter()
+	eng = _engine(device)
+	res = eng.run([VD], CP, [CP['out_ratio']], detail=True, want_filtered=True, cvrg_window=cvrg_window,
+				raise_on_clip_error=False)[0]
+	t_total = time.perf_counter() - t0
+	t_map = eng.ctx.last_map_kernel_ms()[0] / 1000.0
+	if res.status == _cabi.RVB_ERR_NO_CENTRES:
+		# the reference reaches float(None) in interp_handler (smartVidCrop.py:1533)
+		raise TypeError("float() argument must be a string or a real number, not 'NoneType' (no non-empty saliency map)")
+	if res.status != _cabi.RVB_OK:
+		raise _cabi.RvbError(res.status, 'a saliency map has more than %d salient pixels' % _cabi.RVB_MAX_POINTS)
+
+	do_pad = False
+	if CP['exit_on_spread_sal'] and res.mean_sal_score > CP['t_sal']:
+		do_pad = True   # Appendix B-3: compare mean_sal_score (the reference reads an unset key)
+	if CP['exit_on_low_cvrg'] and float(res.cvrg_scores[0]) < CP['t_cvrg']:
+		do_pad = True
+	VD = _fill_vd(VD, CP, res, 0, want_smaps=True)
+	smart_crop_results['cuts_clust'] = 0
+	if do_pad:
+		# Appendix B-2: the reference's pad path raises KeyError('dx'); return the state its
+		# caller anticipates ("Bounding boxes are not available", smartVidCrop.py:2788-2790)
+		for k in ('bbs', 'dx', 'dy', 'dxnf', 'dynf', 'dxi', 'dyi', 'dxl', 'dyl', 'dxs', 'dys', 'ts'):
+			VD.pop(k, None)
+		smart_crop_results['result'] = 'padded'
+	else:
+		smart_crop_results['result'] = 'smart cropped'
+
+	smart_crop_results['info'] = ' (%dx%d)->(%dx%d)->(%dx%d)->(%dx%d)\n' % \
+		(VD['h_orig'], VD['w_orig'], VD['h_process'], VD['w_process'],
+		VD['h_final'], VD['w_final'], VD['fbb_h'], VD['fbb_w'])
+	params_string = ''
+	for cpk in CP.keys():
+		params_string += ' %-18s : %s\n' % (cpk, str(CP[cpk]))
+	smart_crop_results['params'] = params_string
+	smart_crop_results['mean_sal_score'] = VD['mean_sal_score']
+	smart_crop_results['mean_sal_score_t'] = CP['t_sal']
+	smart_crop_results['coverage_score'] = VD['mean_cvrg_score']
+	smart_crop_results['coverage_score_t'] = CP['t_cvrg']
+	t_dict = _times_dict(VD['fc'] / VD['fr'], t_map, t_total, ingest_times)
+	for k in t_dict.keys():
+		if k.startswith('_'):
+			smart_crop_results['t_' + k] = t_dict[k]
+	for k in t_dict.keys():
+		if not k.startswith('_'):
+			smart_crop_results['t_' + k] = t_dict[k]
+	if verbose:
+		print(' Times::')
+		for k, v in t_dict.items():
+			print('   %-21s : %s' % (k, v))
+	gc.collect()
+	return VD, smart_crop_results
+
+
+def write_result_files(results_out, suffix, vid_data, info_dict):
+	"""The two text outputs of the reference's driver (smartVidCrop.py:2778-2785):
+	<suffix>_info.txt (key:value lines) and <suffix>.txt (x1,y1,x2,y2 per frame)."""
+	os.makedirs(results_out, exist_ok=True)
+	with open(os.path.join(results_out, suffix + '_info.txt'), 'w') as stfp:
+		for k in info_dict.keys():
+			stfp.write(k + ':' + str(info_dict[k]) + '\n')
+	with open(os.path.join(results_out, suffix + '.txt'), 'w') as bbfp:
+		for bb in vid_data['bbs']:
+			bbfp.write('%d,%d,%d,%d\n' % (bb[0], bb[1], bb[2], bb[3]))
+
+
+def process_pickles(pickle_paths, results_out_top, aspect_ratios_to_test=('1:3', '3:1'), crop_params=None,
+					test_name='default_config', device=0):
+	"""The reference's batch driver (smartVidCrop.py:2722-2785) over ingest pickles: for every
+	(aspect ratio, video) writes results/<test_name>/<vid>_<a>-<b>.txt and _info.txt.  All
+	ratios of a video are evaluated from one GPU pass."""
+	CP = sc_init_crop_params() if crop_params is None else dict(crop_params)
+	_check_supported(CP)
+	vds = []
+	names = []
+	for pth in pickle_paths:
+		with open(pth, 'rb') as fp:
+			vds.append(pickle.load(fp))
+		names.append(os.path.basename(pth).split('.')[0])
+	t0 = time.perf_counter()
+	eng = _engine(device)
+	results = eng.run(vds, CP, list(aspect_ratios_to_test), detail=True)
+	t_total = time.perf_counter() - t0
+	t_map = eng.ctx.last_map_kernel_ms()[0] / 1000.0
+	results_out = os.path.join(results_out_top, str(test_name))
+	for vd, name, res in zip(vds, names, results):
+		share = float(vd['fc_sel']) / float(sum(v['fc_sel'] for v in vds))
+		for r, orp in enumerate(aspect_ratios_to_test):
+			cp = dict(CP)
+			cp['out_ratio'] = orp
+			VD = _fill_vd(dict(vd), cp, res, r, want_smaps=False)
+			info = {'cuts_clust': 0, 'result': 'smart cropped'}
+			info['info'] = ' (%dx%d)->(%dx%d)->(%dx%d)->(%dx%d)\n' % (VD['h_orig'], VD['w_orig'], VD['h_process'],
+																	VD['w_process'], VD['h_final'], VD['w_final'],
+																	VD['fbb_h'], VD['fbb_w'])
+			t_dict = _times_dict(VD['fc'] / VD['fr'], t_map * share, t_total * share, dict(vd.get('times', {})))
+			for k, v in t_dict.items():
+				info['t_' + k] = v
+			write_result_files(results_out, name + '_' + str(orp.replace(':', '-')), VD, info)
+	return results

@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures produced by the
+unmodified reference and against the oracle.  Needs a GPU: pytest -m gpu."""
+import os
+import statistics
+
+import numpy as np
+import pytest
+
+from helpers import CLIP_NAMES, GOLDEN, load_clip_fixture, loess_tolerance
+
+pytestmark = pytest.mark.gpu
+
+GOLD_1_3 = [0.5063503965471644, 0.5085459028456193, 0.48639442473709943, 0.4985176465467487,
+			0.49074824192623134, 0.5055689465632044]
+GOLD_3_1 = [0.7071752389525412, 0.7247261735288933, 0.7027747813757874, 0.7011597429628194,
+			0.7137894895151101, 0.7360647297774207]
+
+
+@pytest.fixture(scope='module')
+def engine():
+	from retargetvid_b200.engine import CropEngine
+	e = CropEngine(0)
+	yield e
+	e.close()
+
+
+def _eval_fixture():
+	z = np.load(os.path.join(GOLDEN, 'eval_fixture.npz'))
+	vids = [int(v) for v in z['vid_inds']]
+	annots = []
+	for u in range(1, 7):
+		per = {}
+		for ar in ('1-3', '3-1'):
+			boxes = z['annot_%d_%s' % (u, ar)].astype(np.int32)
+			lens = z['annot_len_%d_%s' % (u, ar)]
+			offs = np.concatenate([[0], np.cumsum(lens)])
+			per[ar] = {v: boxes[offs[i]:offs[i + 1]] for i, v in enumerate(vids)}
+		annots.append(per)
+	method = {}
+	for ar in ('1-3', '3-1'):
+		boxes = z['method_%s' % ar].astype(np.int32)
+		lens = z['method_len_%s' % ar]
+		offs = np.concatenate([[0], np.cumsum(lens)])
+		method[ar] = {v: boxes[offs[i]:offs[i + 1]] for i, v in enumerate(vids)}
+	frame_counts = {v: len(annots[0]['1-3'][v]) for v in vids}
+	return method, annots, frame_counts, str(z['eval_csv'])
+
+
+def test_iou_golden_vector(engine):
+	"""Config 2: shipped results vs 6 annotators, every number of BASELINE.md section 2 bit for bit."""
+	from retargetvid_b200 import retargetvid_eval as rev
+	method, annots, frame_counts, csv = _eval_fixture()
+	ev = rev.evaluate_run(engine.ctx, method, annots, frame_counts)
+	assert ev['1-3']['per_user'] == GOLD_1_3
+	assert ev['3-1']['per_user'] == GOLD_3_1
+	assert ev['1-3']['mean'] == 49.93542598610112
+	assert ev['3-1']['mean'] == 71.42816926854287
+	line = csv.splitlines()[-1].split(',')
+	assert ['%05.3f' % ev['1-3'][k] for k in ('worst', 'best', 'mean')] == line[1:4]
+	assert ['%05.3f' % ev['3-1'][k] for k in ('worst', 'best', 'mean')] == line[12:15]
+
+
+def test_iou_per_frame_and_exact_mean_vs_oracle(engine):
+	from oracle import eval_oracle
+	from retargetvid_b200 import retargetvid_eval as rev
+	method, annots, frame_counts, _ = _eval_fixture()
+	vids = sorted(method['1-3'].keys())[:12]
+	sub = {v: method['1-3'][v] for v in vids}
+	ann = [{v: a['1-3'][v] for v in vids} for a in annots]
+	vid_iou, fiou, order = rev.evaluate_arrays(engine.ctx, sub, ann, frame_counts, want_frame_iou=True)
+	off = 0
+	for i, v in enumerate(order):
+		n = frame_counts[v]
+		for u in range(6):
+			ref = [eval_oracle.bb_intersection_over_union(eval_oracle.clamp0(list(ann[u][v][f])),
+														eval_oracle.clamp0(list(sub[v][f]))) for f in range(n)]
+			assert list(fiou[u, off:off + n]) == ref
+			assert vid_iou[i][u] == statistics.mean(ref)
+		off += n
+
+
+def test_iou_edge_cases(engine):
+	"""negative coordinates are clamped, disjoint boxes give 0, short method files stop the mean early."""
+	from oracle import eval_oracle
+	from retargetvid_b200 import retargetvid_eval as rev
+	rng = np.random.default_rng(5)
+	method = {1: rng.integers(-50, 700, (40, 4)).astype(np.int32), 2: np.array([[0, 0, 10, 10]] * 7, dtype=np.int32)}
+	for v in method:
+		method[v][:, 2:] = np.maximum(method[v][:, 2:], method[v][:, :2])
+	annots = [{1: rng.integers(0, 640, (50, 4)).astype(np.int32), 2: np.array([[100, 100, 120, 130]] * 9, dtype=np.int32)}]
+	annots[0][1][:, 2:] = np.maximum(annots[0][1][:, 2:], annots[0][1][:, :2])
+	fc = {1: 50, 2: 9}
+	vid_iou, _, order = rev.evaluate_arrays(engine.ctx, method, annots, fc)
+	for i, v in enumerate(order):
+		assert vid_iou[i][0] == eval_oracle.video_iou([list(b) for b in method[v]], [list(b) for b in annots[0][v]], fc[v])
+
+
+def test_cluster_labels_match_library_fixture(engine):
+	"""sc_clustering_filt's fit_predict (smartVidCrop.py:1099): labels equal to the stand-in library's."""
+	from retargetvid_b200 import _cabi
+	z = np.load(os.path.join(GOLDEN, 'hdbscan_fixture.npz'))
+	bad = []
+	for i in range(int(z['count'])):
+		P = z['P_%d' % i].astype(np.int64)
+		want = z['L_%d' % i].astype(np.int64)
+		mcs, ms = [int(v) for v in z['cfg_%d' % i]]
+		m = np.zeros((140, 250), dtype=np.uint8)
+		m[P[:, 0], P[:, 1]] = 200
+		p = _cabi.rvb_params()
+		engine.ctx.lib.rvb_params_default(p, 0)
+		p.hdbscan_min = mcs
+		p.hdbscan_min_samples = 0 if ms < 0 else ms
+		got = engine.ctx.debug_cluster_labels(p, m)
+		if not np.array_equal(got, want):
+			bad.append((i, len(P), int((got != want).sum())))
+	assert not bad, bad
+
+
+def _nan_close(a, b, tol):
+	a = np.asarray(a, dtype=np.float64)
+	b = np.asarray(b, dtype=np.float64)
+	assert a.shape == b.shape
+	return float(np.max(np.abs(a - b))) if a.size else 0.0
+
+
+@pytest.mark.parametrize('name', CLIP_NAMES)
+def test_clip_fixture_end_to_end(engine, name):
+	"""Every stage output of the reference's smart_vid_crop on a synthetic clip."""
+	from retargetvid_b200 import smartVidCrop as svc
+	vd, over, ratios, fx = load_clip_fixture(name)
+	CP = svc.sc_init_crop_params()
+	CP.update(over)
+	res = engine.run([vd], CP, ratios, detail=True, want_filtered=True)[0]
+	assert res.status == 0
+	# integer stages: bit-exact
+	filt = np.transpose(res.filtered, (1, 2, 0))
+	assert np.array_equal(filt, fx['smaps_filtered']), 'filtered maps differ in %d maps' % int(
+		(filt != fx['smaps_filtered']).any(axis=(0, 1)).sum())
+	for k, r in enumerate(ratios):
+		tag = r.replace(':', '-')
+		assert list(res.dims[k]) == list(fx['dims_' + tag])
+	# float stages: stated tolerances (process pixels)
+	assert _nan_close(res.dx, fx['dx'], 0) <= 1e-9
+	assert _nan_close(res.dy, fx['dy'], 0) <= 1e-9
+	assert _nan_close(res.series[0], fx['dxi'], 0) <= 1e-9
+	assert _nan_close(res.series[1], fx['dyi'], 0) <= 1e-9
+	assert _nan_close(res.series[2], fx['dxl'], 0) <= 1e-8
+	assert _nan_close(res.series[3], fx['dyl'], 0) <= 1e-8
+	max_cl = int(max(s[1] - s[0] + 1 for s in vd['segmentation']))
+	tol = max(loess_tolerance(max_cl), 1e-8)
+	assert _nan_close(res.series[4], fx['dxs_pre'], 0) <= tol
+	assert _nan_close(res.series[5], fx['dys_pre'], 0) <= tol
+	# boxes: bit-exact, except frames whose reference centre sits within tol of an integer
+	# boundary before the int() truncation (smartVidCrop.py:998-999) -- enumerated, must be explained
+	scale_w = vd['w_process'] / vd['w_orig']
+	scale_h = vd['h_process'] / vd['h_orig']
+	for k, r in enumerate(ratios):
+		want = fx['bbs_' + r.replace(':', '-')]
+		got = res.boxes[k]
+		diff = np.nonzero((got != want).any(axis=1))[0]
+		for f in diff:
+			vx = fx['dxs_pre'][f] / scale_w
+			vy = fx['dys_pre'][f] / scale_h
+			near = min(abs(vx - round(vx)), abs(vy - round(vy)))
+			assert near <= tol / min(scale_w, scale_h), (name, r, int(f), got[f], want[f])
+			assert np.max(np.abs(got[f] - want[f])) <= 1
+		assert len(diff) <= max(1, len(want) // 100), (name, r, len(diff))
+
+
+def test_smooth_series_vs_pyloess_fixture(engine):
+	"""loess_handler -> pyloess.Loess.estimate (pyloess.py:61-95), degree 2, as the hot path calls it."""
+	from retargetvid_b200 import _cabi
+	z = np.load(os.path.join(GOLDEN, 'loess_fixture.npz'))
+	for cl in (12, 60, 300, 1283):
+		y = z['y_%d' % cl]
+		want = z['est_%d' % cl]
+		w = int(z['w_%d' % cl])
+		p = _cabi.rvb_params()
+		engine.ctx.lib.rvb_params_default(p, 0)
+		p.lp_filt = 0
+		# window = min(int(fr * w_secs), cl - 2), made odd: pick fr so that it equals the fixture's
+		p.loess_w_secs = 1.0
+		fr = float(w) if w % 2 == 1 else float(w + 1)
+		lp, sm = engine.ctx.debug_smooth_series(p, y, fr)
+		assert np.array_equal(lp, y)
+		assert np.max(np.abs(sm - want)) <= loess_tolerance(cl), (cl, np.max(np.abs(sm - want)))
+
+
+def test_batch_equals_single(engine):
+	"""Batching many clips and ratios in one launch gives exactly the per-clip results."""
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vds = [synth.make_clip(900 + i, fc=60 + 17 * i, shot_starts=[30] if i % 2 else []) for i in range(5)]
+	CP = svc.sc_init_crop_params()
+	ratios = ['1:3', '3:1', '9:16', '4:5']
+	batch = engine.run(vds, CP, ratios)
+	for i, vd in enumerate(vds):
+		one = engine.run([vd], CP, ratios)[0]
+		assert np.array_equal(one.boxes, batch[i].boxes)
+		assert np.array_equal(one.dx, batch[i].dx)
+		assert np.array_equal(one.series, batch[i].series)
+
+
+def test_drop_in_smart_vid_crop(engine, tmp_path):
+	"""The reference-facing call: vid_data pickle in temp_path -> (VD, smart_crop_results) and the text files."""
+	import pickle
+	from retargetvid_b200 import smartVidCrop as svc
+	vd, over, ratios, fx = load_clip_fixture('c1_default')
+	with open(os.path.join(tmp_path, 'clipA.pkl'), 'wb') as fp:
+		pickle.dump(vd, fp)
+	CP = svc.sc_init_crop_params()
+	CP['out_ratio'] = '1:3'
+	VD, res = svc.smart_vid_crop(os.path.join('somewhere', 'clipA.mp4'), CP, temp_path=str(tmp_path), save_vid=False)
+	assert res['result'] == 'smart cropped'
+	assert VD['bbs'] == [[int(v) for v in bb] for bb in fx['bbs_1-3']]
+	assert res['info'] == ' (360x640)->(140x250)->(360x120)->(360x120)\n'
+	assert isinstance(VD['bbs'][0][0], int) and 't__clustering' in res and 't_total' in res
+	svc.write_result_files(str(tmp_path), 'clipA_1-3', VD, res)
+	with open(os.path.join(tmp_path, 'clipA_1-3.txt')) as fp:
+		lines = fp.read().splitlines()
+	assert lines[0] == '%d,%d,%d,%d' % tuple(fx['bbs_1-3'][0]) and len(lines) == vd['fc']
+
+
+def test_error_behaviour(engine):
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	CP = svc.sc_init_crop_params()
+	with pytest.raises(TypeError):  # the reference raises TypeError (float(None)) when every map is empty
+		svc.smart_vid_crop('x.mp4', CP, save_vid=False, vid_data=synth.make_clip(1, fc=60, kind='empty'))
+	CP2 = dict(CP)
+	CP2['t_threshold'] = 0      # every pixel salient: far beyond RVB_MAX_POINTS -> loud capacity error
+	with pytest.raises(_cabi.RvbError) as ei:
+		svc.smart_vid_crop('x.mp4', CP2, save_vid=False, vid_data=synth.make_clip(2, fc=30))
+	assert ei.value.code == _cabi.RVB_ERR_CAPACITY
+	with pytest.raises(NotImplementedError):
+		svc.smart_vid_crop('x.mp4', svc.sc_init_crop_params(use_best_settings=True), save_vid=False,
+						vid_data=synth.make_clip(3, fc=30))
