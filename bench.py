@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the saliency-map -> crop-track hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--clips C]
+
+A step is one pass of the hot path over one batch of synthetic DHF1K-shaped clips
+(BASELINE.json configs[2]: 200 clips x {1:3, 3:1}); with N GPUs every rank gets its own
+batch of the same shape (weak scaling, videos are independent, no collective on the data
+path).  `value` is device-resident throughput, `e2e` goes through the C ABI with pinned
+HOST buffers in the reference's own [H,W,N] layout (H2D + D2H inside the timed region).
+`--impl reference` times the CPU restatement of the reference's path (the oracle, with
+the clustering delegated to scikit-learn's HDBSCAN as in the survey) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATIOS = ['1:3', '3:1']
+METRIC = 'saliency-map->crop frames/sec (boxes produced: frames x target ratios)'
+UNIT = 'frames/s'
+H, W, WPS = 140, 250, 256
+ALGO_BYTES_PER_MAP = H * W + 17          # uint8 entry, + the (cx, cy, empty) record
+ALGO_BYTES_PER_BOX = 16
+
+
+def _make(spec):
+	from retargetvid_b200 import synth
+	return synth.make_clip(**spec)
+
+
+def make_workload(n_clips, rank):
+	from retargetvid_b200 import synth
+	specs = synth.config_clips(3, n_clips=n_clips, rank=rank)
+	procs = min(len(specs), max(1, (os.cpu_count() or 1)))
+	if procs > 1:
+		with mp.get_context('fork').Pool(procs) as pool:
+			return pool.map(_make, specs, chunksize=4)
+	return [_make(s) for s in specs]
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a restatement of the reference's path), all host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_one(args):
+	import warnings
+	warnings.filterwarnings('ignore')
+	from oracle import sc_oracle
+	from sklearn.cluster import HDBSCAN
+	vd, ratio = args
+	CP = sc_oracle.sc_init_crop_params()
+	CP['out_ratio'] = ratio
+	k = CP['hdbscan_min'] if CP['hdbscan_min_samples'] is None else CP['hdbscan_min_samples']
+	clusterer = HDBSCAN(min_cluster_size=CP['hdbscan_min'], min_samples=k + 1, metric='sqeuclidean',
+						algorithm='brute', cluster_selection_method='eom', allow_single_cluster=True, copy=True)
+
+	def cluster_fn(X):
+		return clusterer.fit_predict(np.asarray(X, dtype=np.float64))
+	out = sc_oracle.smart_vid_crop_oracle(vd, CP, cluster_fn=cluster_fn)
+	return len(out['bbs'])
+
+
+def cpu_baseline(vds, n_sample, steps=1, warmup=0, budget_s=150.0):
+	"""Times the CPU path on a bounded sample: the first n_sample clips x one ratio, one clip
+	per process, all cores.  The sample shrinks if steps x warmup passes would exceed the
+	time budget.  Returns (frames/s, cores, description, seconds per step)."""
+	cores = os.cpu_count() or 1
+	sample = [(vd, RATIOS[0]) for vd in vds[:n_sample]]
+	procs = min(cores, len(sample))
+	with mp.get_context('fork').Pool(procs) as pool:
+		t0 = time.perf_counter()
+		pool.map(_cpu_one, sample, chunksize=1)          # untimed: imports, first-call costs
+		t1 = time.perf_counter() - t0
+		passes = steps + max(0, warmup - 1)
+		if passes * t1 > budget_s and len(sample) > procs:
+			keep = max(procs, int(len(sample) * budget_s / (passes * t1)))
+			sample = sample[:keep]
+		for _ in range(max(0, warmup - 1)):
+			pool.map(_cpu_one, sample, chunksize=1)
+		t0 = time.perf_counter()
+		for _ in range(steps):
+			pool.map(_cpu_one, sample, chunksize=1)
+		dt = (time.perf_counter() - t0) / steps
+	frames = sum(vd['fc'] for vd, _ in sample)
+	maps = sum(vd['fc_sel'] for vd, _ in sample)
+	desc = ('first %d clips of the workload x ratio %s (%d frames, %d maps) per step, one clip per process on '
+			'%d host cores; oracle/sc_oracle.py with sklearn.cluster.HDBSCAN(brute) as the clustering library'
+			% (len(sample), RATIOS[0], frames, maps, procs))
+	return frames / dt, procs, desc, dt
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+	def __init__(self, index):
+		self.index = index
+		self.proc = None
+		self.path = None
+
+	def start(self):
+		try:
+			fd, self.path = tempfile.mkstemp(suffix='.csv')
+			os.close(fd)
+			q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+				'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+				'clocks_event_reasons.sw_power_cap')
+			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+										'--format=csv,noheader,nounits', '-lms', '100'],
+										stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+		except Exception:
+			self.proc = None
+
+	def stop(self):
+		out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+		if self.proc is None:
+			return out
+		self.proc.terminate()
+		try:
+			self.proc.wait(timeout=5)
+		except Exception:
+			self.proc.kill()
+		try:
+			rows = [l.strip().split(', ') for l in open(self.path) if l.strip()]
+			sm = sorted(float(r[0]) for r in rows if len(r) >= 7)
+			if sm:
+				out['sm_mhz'] = sm[len(sm) // 2]
+				out['sm_max_mhz'] = float(rows[0][1])
+				names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+				for k, nme in enumerate(names):
+					if any(r[3 + k].strip().lower().startswith('active') for r in rows if len(r) >= 7):
+						out['reasons'].append(nme)
+				out['samples'] = len(sm)
+			os.unlink(self.path)
+		except Exception:
+			pass
+		return out
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def gpu_arm(args, rank, world, local_rank):
+	import torch
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	torch.cuda.set_device(local_rank)
+	dist = None
+	if world > 1:
+		import torch.distributed as dist
+		dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+	vds = make_workload(args.clips, rank)
+	nc = len(vds)
+	R = len(RATIOS)
+	NM = sum(v['fc_sel'] for v in vds)
+	NF = sum(v['fc'] for v in vds)
+	NS = sum(len(v['segmentation']) for v in vds)
+
+	ctx = _cabi.Context(local_rank)
+	# a real (non-default) stream shared by torch and the library, so that torch's CUDA events bracket the library's work
+	stream = torch.cuda.Stream()
+	torch.cuda.set_stream(stream)
+	ctx.set_stream(stream.cuda_stream)
+	CP = svc.sc_init_crop_params()
+	params = _cabi.params_from_crop_params(CP)
+
+	# metadata (host, as the ABI requires)
+	clips = (_cabi.rvb_clip * nc)()
+	shots = np.zeros((NS, 4), dtype=np.int32)
+	tinds = np.zeros(NM, dtype=np.int32)
+	mo = fo = so = 0
+	for i, vd in enumerate(vds):
+		c = clips[i]
+		c.n_maps, c.n_frames, c.n_shots = vd['fc_sel'], vd['fc'], len(vd['segmentation'])
+		c.h_orig, c.w_orig, c.fr = vd['h_orig'], vd['w_orig'], vd['fr']
+		c.map_offset, c.frame_offset, c.shot_offset = mo, fo, so
+		shots[so:so + c.n_shots, 0:2] = vd['segmentation']
+		shots[so:so + c.n_shots, 2:4] = vd['segmentation_sel']
+		tinds[mo:mo + c.n_maps] = vd['true_inds']
+		mo += c.n_maps
+		fo += c.n_frames
+		so += c.n_shots
+
+	# e2e input: pinned host memory, reference layout [H,W,N] per clip, packed back to back
+	host_maps = torch.empty(NM * H * W, dtype=torch.uint8).pin_memory()
+	hm = host_maps.numpy()
+	ptrs = (C.c_void_p * nc)()
+	off = 0
+	for i, vd in enumerate(vds):
+		n = vd['fc_sel'] * H * W
+		hm[off:off + n] = vd['smaps'].reshape(-1)
+		ptrs[i] = host_maps.data_ptr() + off
+		off += n
+	host_boxes = torch.empty((R, NF, 4), dtype=torch.int32).pin_memory()
+
+	# device-resident input: device-native layout uint8 [N][H][256]
+	dev_maps = torch.zeros((NM, H, WPS), dtype=torch.uint8, device='cuda')
+	mo = 0
+	for vd in vds:
+		n = vd['fc_sel']
+		dev_maps[mo:mo + n, :, :W] = torch.from_numpy(np.ascontiguousarray(np.transpose(vd['smaps'], (2, 0, 1)))).cuda()
+		mo += n
+	dev_boxes = torch.empty((R, NF, 4), dtype=torch.int32, device='cuda')
+	torch.cuda.synchronize()
+
+	def batch(device_resident):
+		b = _cabi.rvb_batch()
+		b.n_clips, b.h_process, b.w_process, b.n_ratios = nc, H, W, R
+		for r, s in enumerate(RATIOS):
+			a, bb = s.split(':')
+			b.ratio_w[r], b.ratio_h[r] = float(a), float(bb)
+		b.clips = clips
+		b.shots = shots.ctypes.data
+		b.true_inds = tinds.ctypes.data
+		if device_resident:
+			b.maps_kind, b.mem_space, b.row_stride = _cabi.RVB_MAPS_U8_NHW, _cabi.RVB_MEM_DEVICE, WPS
+			b.maps = dev_maps.data_ptr()
+			b.boxes = dev_boxes.data_ptr()
+		else:
+			b.maps_kind, b.mem_space = _cabi.RVB_MAPS_U8_HWN, _cabi.RVB_MEM_HOST
+			b.maps = None
+			b.clip_maps = ptrs
+			b.boxes = host_boxes.data_ptr()
+		return b
+
+	b_dev, b_host = batch(True), batch(False)
+
+	def barrier():
+		if dist is not None:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	def timed(b, steps, collect_map_ms=False):
+		barrier()
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		l0 = ctx.launch_count()
+		map_ms, map_launches = 0.0, 0
+		e0.record()
+		for _ in range(steps):
+			ctx.crop_track_batch(params, b)
+			if collect_map_ms:
+				ms, nl = ctx.last_map_kernel_ms()   # waits for this step's map kernels only
+				map_ms += ms
+				map_launches += nl
+		e1.record()
+		barrier()
+		ms = e0.elapsed_time(e1)
+		if dist is not None:
+			t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+			ms = float(t.item())
+		return ms, ctx.launch_count() - l0, map_ms, map_launches
+
+	for _ in range(args.warmup):
+		ctx.crop_track_batch(params, b_dev)
+	for _ in range(max(1, args.warmup // 2)):
+		ctx.crop_track_batch(params, b_host)
+	torch.cuda.synchronize()
+	first_boxes = dev_boxes.cpu().numpy().copy()
+	assert np.array_equal(first_boxes, host_boxes.numpy()), 'device-resident and host-buffer paths disagree'
+
+	sampler = ClockSampler(local_rank)
+	if rank == 0:
+		sampler.start()
+	ms_dev, launches, _, _ = timed(b_dev, args.steps)
+	ms_e2e, _, _, _ = timed(b_host, args.steps)
+	clocks = sampler.stop() if rank == 0 else None
+	# roofline of the dominant kernel (the fused map kernel family): its own CUDA events, separate
+	# pass so that waiting on the events does not perturb the throughput numbers above
+	_, _, map_ms, map_launches = timed(b_dev, args.steps, collect_map_ms=True)
+
+	if args.phases and rank == 0:
+		ctx.phase_cycles(True)
+		ctx.crop_track_batch(params, b_dev)
+		cyc = ctx.phase_cycles(False)
+		names = ['load', 'threshold+compact', 'core distances', 'prim', 'argsort emulation', 'cartesian tree',
+				'condensed bfs', 'fall-out', 'eom+labels', 'rebuild+closing', 'results']
+		tot = float(sum(cyc)) or 1.0
+		sys.stderr.write('map kernel phase split (SM cycles summed over CTAs):\n')
+		for nme, v in zip(names, cyc):
+			sys.stderr.write('  %-20s %14d  %5.1f%%\n' % (nme, v, 100.0 * v / tot))
+	frames_per_step = NF * R
+	value = world * frames_per_step * args.steps / (ms_dev / 1e3)
+	e2e = world * frames_per_step * args.steps / (ms_e2e / 1e3)
+	line = None
+	if rank == 0:
+		peaks = {}
+		try:
+			peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+		except Exception:
+			pass
+		peak = float(peaks.get('hbm_gbs', 6650.0))
+		algo = NM * ALGO_BYTES_PER_MAP
+		achieved = algo * args.steps / (map_ms / 1e3) / 1e9
+		traffic = None
+		try:
+			prof = json.load(open(os.path.join(ROOT, 'profiles', 'map_kernel_traffic.json')))
+			traffic = prof.get('dram_bytes_per_step')
+		except Exception:
+			pass
+		cpu_v, cpu_cores, cpu_desc, _ = cpu_baseline(vds, args.cpu_sample) if world == 1 else (None, None, None, None)
+		line = {
+			'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+			'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+			'dtype': 'u8 maps / int32 lattice arithmetic / f64 track', 'data': 'synthetic',
+			'config': {'workload': 'BASELINE.json configs[2]: %d synthetic DHF1K-shaped 640x360 clips per GPU x ratios %s, '
+								'default (ICIP-2021) crop params' % (nc, ','.join(RATIOS)),
+					'clips_per_gpu': nc, 'frames_per_gpu': NF, 'maps_per_gpu': NM, 'ratios': RATIOS,
+					'maps_per_sec': world * NM * args.steps / (ms_dev / 1e3),
+					'input_bytes_per_gpu': NM * H * WPS, 'l2': 'inputs larger than L2 (no flush needed)',
+					'value_entry': 'device-resident uint8 [N][140][256]', 'e2e_entry': 'pinned host uint8 [H][W][N] per clip'},
+			'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(NM * H * W), 'd2h_bytes_per_step': int(R * NF * 16),
+					'ms_per_step': ms_e2e / args.steps},
+			'gpu_launches': int(launches),
+			'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+						'traffic': traffic, 'kernel': 'rvb::map_kernel<NT,TPT> (all capacity classes and waves of a step)',
+						'algorithmic_bytes_per_step': algo, 'kernel_ms_per_step': map_ms / args.steps,
+						'kernel_launches_per_step': map_launches / args.steps,
+						'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'},
+			'clocks': clocks,
+		}
+		if cpu_v is not None:
+			line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cpu_cores, 'kind': 'port', 'sample': cpu_desc}
+	if dist is not None:
+		dist.barrier()
+		dist.destroy_process_group()
+	ctx.close()
+	return line
+
+
+def reference_arm(args, rank, world):
+	if rank != 0:
+		return None
+	vds = make_workload(max(args.cpu_sample, 1), 0)
+	v, cores, desc, dt = cpu_baseline(vds, args.cpu_sample, steps=args.steps, warmup=args.warmup)
+	NM = sum(x['fc_sel'] for x in vds[:args.cpu_sample])
+	NF = sum(x['fc'] for x in vds[:args.cpu_sample])
+	return {
+		'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+		'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+		'dtype': 'u8 maps / f64 (numpy, scipy, scikit-learn on the CPU)', 'data': 'synthetic',
+		'config': {'workload': 'BASELINE.json configs[2] (bounded sample of the same clips): %d clips x ratio %s per step'
+							% (args.cpu_sample, RATIOS[0]), 'frames_per_step': NF, 'maps_per_step': NM},
+		'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+		'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+		'gpu_launches': 0,
+	}
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument('--gpus', type=int, default=1)
+	ap.add_argument('--steps', type=int, default=5)
+	ap.add_argument('--warmup', type=int, default=3)
+	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+	ap.add_argument('--clips', type=int, default=200, help='clips per GPU (BASELINE configs[2]: 200)')
+	ap.add_argument('--cpu-sample', type=int, default=16, help='clips in the bounded CPU sample')
+	ap.add_argument('--phases', action='store_true', help='also print the per-phase SM-cycle split of the map kernel (stderr)')
+	args = ap.parse_args()
+	rank = int(os.environ.get('RANK', '0'))
+	world = int(os.environ.get('WORLD_SIZE', '1'))
+	local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+	if args.impl == 'reference':
+		line = reference_arm(args, rank, world)
+	else:
+		if args.warmup < 3:
+			args.warmup = 3
+		line = gpu_arm(args, rank, world, local_rank)
+	if rank == 0 and line is not None:
+		print(json.dumps(line))
+
+
+if __name__ == '__main__':
+	main()

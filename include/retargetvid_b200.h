@@ -145,6 +145,11 @@ int64_t rvb_ctx_launch_count(const rvb_ctx *ctx);
  * kernel) summed over the last crop_track call; valid after a synchronise */
 int rvb_ctx_last_map_kernel_ms(rvb_ctx *ctx, float *ms, int32_t *launches);
 
+/* profiling aid: when enabled, the map kernel accumulates SM cycles per phase (11 phases: load, threshold+compact,
+ * core distances, Prim, argsort emulation, Cartesian tree, condensed-tree BFS, fall-out, EOM+labels, rebuild+closing,
+ * results), summed over CTAs since the last call of this function */
+int rvb_ctx_phase_cycles(rvb_ctx *ctx, int enable, uint64_t out[16]);
+
 /* replaces sc_init_crop_params(use_best_settings) -- smartVidCrop.py:132-209 */
 int rvb_params_default(rvb_params *p, int use_best_settings);
 

@@ -30,7 +30,7 @@ RVB_MAPS_F32_NHW = 2
 EXPORTS = ['rvb_version', 'rvb_last_error', 'rvb_ctx_create', 'rvb_ctx_destroy', 'rvb_ctx_set_stream',
 		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_params_default',
 		'rvb_crop_track_batch', 'rvb_iou_batch_run', 'rvb_iou_mean_from_acc', 'rvb_debug_cluster_labels',
-		'rvb_debug_smooth_series']
+		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles']
 
 
 class RvbError(RuntimeError):
@@ -95,6 +95,7 @@ def load_library():
 	lib.rvb_ctx_launch_count.restype = C.c_int64
 	lib.rvb_ctx_last_map_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
 	lib.rvb_params_default.argtypes = [C.POINTER(rvb_params), C.c_int]
+	lib.rvb_ctx_phase_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
 	lib.rvb_crop_track_batch.argtypes = [C.c_void_p, C.POINTER(rvb_params), C.POINTER(rvb_batch)]
 	lib.rvb_iou_batch_run.argtypes = [C.c_void_p, C.POINTER(rvb_iou_batch)]
 	lib.rvb_iou_mean_from_acc.argtypes = [C.POINTER(C.c_uint64), C.c_int64]
@@ -172,6 +173,11 @@ class Context(object):
 		n = C.c_int32()
 		check(self.lib.rvb_ctx_last_map_kernel_ms(self.handle, C.byref(ms), C.byref(n)))
 		return float(ms.value), int(n.value)
+
+	def phase_cycles(self, enable=True):
+		out = (C.c_uint64 * 16)()
+		check(self.lib.rvb_ctx_phase_cycles(self.handle, 1 if enable else 0, out))
+		return [int(v) for v in out]
 
 	def crop_track_batch(self, params, batch):
 		check(self.lib.rvb_crop_track_batch(self.handle, C.byref(params), C.byref(batch)))

@@ -107,6 +107,7 @@ struct MapArgs {
 	const int *cvrg_cfg;       // [n_clips][R][2] = (mode, window) or null
 	int n_ratios;
 	int32_t *labels_dbg;       // optional: labels of the single map being debugged
+	unsigned long long *phase_cycles;  // optional [16]: SM cycles spent per phase, summed over CTAs (profiling aid)
 	// params
 	int t_threshold, clust_filt, mcs, min_samples, select_sum, op_close, com_km;
 	SmemLayout lay;
@@ -414,6 +415,15 @@ struct MapScalars {
 	uint32_t argmax_key;
 };
 
+#define RVB_PHASE(k)                                                              \
+	do {                                                                          \
+		if (a.phase_cycles != nullptr && threadIdx.x == 0) {                      \
+			const long long now_ = clock64();                                     \
+			atomicAdd(&a.phase_cycles[k], (unsigned long long)(now_ - phase_t0)); \
+			phase_t0 = now_;                                                      \
+		}                                                                         \
+	} while (0)
+
 template <int NT, int TPT>
 __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -446,6 +456,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 		__syncthreads();
 		const int m = S.map_idx;
 		if (m < 0) break;
+		long long phase_t0 = clock64();
 		MapOut res;
 		res.cx = 0.0; res.cy = 0.0; res.raw_sum = 0; res.n_points = 0; res.n_clusters = -1;
 		res.kept_points = 0; res.flags = 0; res.pad = 0;
@@ -505,6 +516,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 		}
 		__syncthreads();
 
+		RVB_PHASE(0);  // load
 		// raw statistics, threshold, blend -- one pass over the words
 		{
 			const int pred = a.pred ? a.pred[m] : -1;
@@ -569,6 +581,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 		}
 		res.n_points = n;
 		__syncthreads();
+		RVB_PHASE(1);  // threshold + compaction
 		if (n > L.nmax) {
 			// does not fit this launch's capacity: hand it to the next size class
 			if (tid == 0) {
@@ -678,6 +691,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 				__syncthreads();
 			}
 
+			RVB_PHASE(2);  // core distances
 			// ---- phase 3: Prim on the mutual-reachability graph -------------------------------------
 			// from point 0, lowest index wins ties (np.argmin), _linkage.pyx:97-112.  Each thread keeps
 			// its TPT points in registers; key = (min reachability << 13) | index.
@@ -739,6 +753,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			}
 			__syncthreads();
 
+			RVB_PHASE(3);  // Prim
 			// ---- phase 4a: numpy's unstable argsort of the edge weights ------------------------------
 			const int ne = n - 1;
 			for (int e = tid; e < ne; e += NT) skey[e] = (wp[e] << kKeyShift) | (uint32_t)e;
@@ -749,6 +764,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			if (tid == 0) S.root_edge = skey[ne - 1] & kKeyIdxMask;
 			__syncthreads();
 
+			RVB_PHASE(4);  // argsort emulation
 			// ---- phase 4b: the dendrogram as a Cartesian tree over Prim positions --------------------
 			// Edge e joins positions e and e+1 at time rank[e]; at that time its cluster is the maximal
 			// interval around e whose edges all have smaller rank (make_single_linkage, _linkage.pyx:226).
@@ -786,6 +802,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			}
 			__syncthreads();
 
+			RVB_PHASE(5);  // Cartesian tree
 			// ---- phase 4c: condensed tree over the big nodes, breadth first (_condense_tree) ---------
 			// rank[] is dead from here: its storage becomes relabel[]
 			const int mcs = a.mcs;
@@ -837,6 +854,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 				continue;
 			}
 
+			RVB_PHASE(6);  // condensed-tree BFS
 			// ---- phase 4d: where each point falls out (the queue storage becomes pcl[]) --------------
 			for (int q = tid; q < n; q += NT) {
 				int node = pl[q];
@@ -850,6 +868,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			}
 			__syncthreads();
 
+			RVB_PHASE(7);  // fall-out
 			// ---- phase 4e: excess of mass, allow_single_cluster=True (_get_clusters) -----------------
 			if (tid == 0) {
 				const int ncl = S.ncl;
@@ -909,6 +928,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			}
 			__syncthreads();
 
+			RVB_PHASE(8);  // EOM + labels + dominant cluster
 			// ---- phase 5: rebuild the map, close it --------------------------------------------------
 			for (int i = tid; i < n_words; i += NT) map32[i] = 0u;
 			__syncthreads();
@@ -928,6 +948,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 		}
 		(void)rebuilt;
 
+		RVB_PHASE(9);  // rebuild + closing
 		// ---- phase 6: results -------------------------------------------------------------------------
 		if (tid == 0) { S.sx = 0ull; S.sy = 0ull; S.cnt = 0u; S.tot = 0u; S.argmax_key = 0u; }
 		__syncthreads();
@@ -1017,6 +1038,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			}
 		}
 		if (tid == 0) a.out[m] = res;
+		RVB_PHASE(10);  // results
 	}
 }
 

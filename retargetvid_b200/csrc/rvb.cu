@@ -91,6 +91,8 @@ struct rvb_ctx {
 	bool map_timed = false;
 	int map_launches = 0;
 	int64_t launches = 0;
+	bool phase_on = false;
+	DevBuf phase;
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
 	PinBuf stage, stage_out;
 };
@@ -324,6 +326,20 @@ extern "C" int rvb_ctx_last_map_kernel_ms(rvb_ctx *c, float *ms, int32_t *launch
 	CU(cudaEventElapsedTime(&t, c->ev_map0, c->ev_map1));
 	if (ms) *ms = t;
 	if (launches) *launches = c->map_launches;
+	return RVB_OK;
+}
+
+extern "C" int rvb_ctx_phase_cycles(rvb_ctx *c, int enable, uint64_t out[16]) {
+	if (!c) return fail(RVB_ERR_INVALID, "ctx is NULL");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	if (c->phase.ensure(16 * sizeof(uint64_t))) return RVB_ERR_CUDA;
+	if (out) {
+		if (c->phase_on) CU(cudaMemcpy(out, c->phase.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+		else memset(out, 0, 16 * sizeof(uint64_t));
+	}
+	CU(cudaMemset(c->phase.p, 0, 16 * sizeof(uint64_t)));
+	c->phase_on = enable != 0;
 	return RVB_OK;
 }
 
@@ -613,6 +629,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.border_prof = nullptr;
 	a.cvrg_cfg = p->exit_on_low_cvrg ? (const int *)(M + o_cvrg) : nullptr;
 	a.n_ratios = R; a.labels_dbg = nullptr;
+	a.phase_cycles = c->phase_on ? (unsigned long long *)c->phase.p : nullptr;
 	a.t_threshold = p->t_threshold; a.clust_filt = p->clust_filt; a.mcs = p->hdbscan_min;
 	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
 	c->map_launches = 0;
