@@ -100,6 +100,7 @@ struct MapArgs {
 	const int *pred;           // slot (in filt) of the predecessor whose filtered map is blended in, or -1
 	const int *store;          // slot (in filt) to write this map's filtered result to, or -1
 	const int *map_clip;       // clip index of a map
+	const uint8_t *chain_next; // 1: map m+1 blends with this map's result -> the same CTA continues with m+1
 	uint8_t *filt;             // [slots][H][fstride]
 	int fstride;
 	MapOut *out;
@@ -301,6 +302,154 @@ __device__ void np_aquicksort(uint32_t *t, int num) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same permutation computed by the whole CTA.  The recursion tree of aquicksort_ is processed
+// level by level, one warp per range: sub-ranges are independent, and one Hoare partition has a
+// closed form -- the scan from the left stops at the positions (ascending) whose key is >= pivot,
+// the scan from the right at the positions (descending) whose key is <= pivot, the r-th stops are
+// exchanged while the left one is still left of the right one, and the final left pointer is
+// min(next left stop, last right stop).  Ranges of <= 16 elements are insertion-sorted by numpy,
+// i.e. sorted stably.  Only ranges numpy POPS from its stack check the depth budget (heapsort).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_stable_small_sort(uint32_t *t, int lo, int hi) {
+	const int lane = threadIdx.x & 31;
+	const int sz = hi - lo + 1;  // 2..16
+	uint32_t x = 0;
+	int rk = 0;
+	if (lane < sz) {
+		x = t[lo + lane];
+		for (int m = 0; m < sz; ++m) {
+			const uint32_t o = t[lo + m];
+			rk += (key_less(o, x) || (!key_less(x, o) && m < lane)) ? 1 : 0;
+		}
+	}
+	__syncwarp();
+	if (lane < sz) t[lo + rk] = x;
+	__syncwarp();
+}
+
+// returns the final pivot position
+__device__ __forceinline__ int warp_partition(uint32_t *t, int pl, int pr, uint16_t *ilist, uint16_t *jlist) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	if (lane == 0) {
+		const int pm = pl + ((pr - pl) >> 1);
+		uint32_t vl = t[pl], vm = t[pm], vr = t[pr];
+		if (key_less(vm, vl)) { uint32_t q = vm; vm = vl; vl = q; }
+		if (key_less(vr, vm)) { uint32_t q = vr; vr = vm; vm = q; }
+		if (key_less(vm, vl)) { uint32_t q = vm; vm = vl; vl = q; }
+		t[pl] = vl;
+		t[pr] = vr;
+		t[pm] = t[pr - 1];
+		t[pr - 1] = vm;
+	}
+	__syncwarp();
+	const uint32_t vp = t[pr - 1];
+	uint16_t *il = ilist + pl, *jl = jlist + pl;
+	int nI = 0, nJ = 0;
+	for (int base = pl + 1; base <= pr - 1; base += 32) {
+		const int p = base + lane;
+		const bool f = (p <= pr - 1) && !key_less(t[p], vp);
+		const uint32_t m = __ballot_sync(0xffffffffu, f);
+		if (f) il[nI + __popc(m & lt_mask)] = (uint16_t)p;
+		nI += __popc(m);
+	}
+	for (int base = pr - 2; base >= pl; base -= 32) {
+		const int p = base - lane;
+		const bool f = (p >= pl) && !key_less(vp, t[p]);
+		const uint32_t m = __ballot_sync(0xffffffffu, f);
+		if (f) jl[nJ + __popc(m & lt_mask)] = (uint16_t)p;
+		nJ += __popc(m);
+	}
+	__syncwarp();
+	const int R = min(nI, nJ);
+	int S = 0;  // number of exchanges: the prefix of r with il[r] < jl[r]
+	for (int base = 0; base < R; base += 32) {
+		const int r = base + lane;
+		const bool f = (r < R) && (il[r] < jl[r]);
+		S += __popc(__ballot_sync(0xffffffffu, f));
+	}
+	for (int r = lane; r < S; r += 32) {
+		const int a = il[r], b = jl[r];
+		const uint32_t q = t[a];
+		t[a] = t[b];
+		t[b] = q;
+	}
+	__syncwarp();
+	const int nextI = (S < nI) ? (int)il[S] : 0x7fffffff;
+	const int lastJ = (S >= 1) ? (int)jl[S - 1] : (pr - 1);
+	const int pi = min(nextI, lastJ);
+	if (lane == 0) {
+		const uint32_t q = t[pi];
+		t[pi] = t[pr - 1];
+		t[pr - 1] = q;
+	}
+	__syncwarp();
+	return pi;
+}
+
+template <int NT>
+__device__ void np_aquicksort_block(uint32_t *t, int num, uint16_t *ilist, uint16_t *jlist, uint16_t *qbuf, int qcap,
+									int *cnt /* shared int[2] */) {
+	constexpr int NW = NT / 32;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (num < 2) return;
+	if (num <= 16) {
+		if (warp == 0) warp_stable_small_sort(t, 0, num - 1);
+		__syncthreads();
+		return;
+	}
+	// range lists: entries of 3 u16 = (pl, pr, depth + 256 | popped << 15)
+	uint16_t *qa = qbuf, *qb = qbuf + 3 * qcap;
+	if (threadIdx.x == 0) {
+		qa[0] = 0;
+		qa[1] = (uint16_t)(num - 1);
+		qa[2] = (uint16_t)(((31 - __clz(num)) * 2 + 256) | 0x8000);
+		cnt[0] = 1;
+		cnt[1] = 0;
+	}
+	__syncthreads();
+	int cur = 0;
+	while (true) {
+		const int ncur = cnt[cur];
+		if (ncur == 0) break;
+		uint16_t *qc = cur ? qb : qa, *qn = cur ? qa : qb;
+		for (int e = warp; e < ncur; e += NW) {
+			int pl = qc[3 * e], pr = qc[3 * e + 1];
+			int depth = (int)(qc[3 * e + 2] & 0x7FFF) - 256;
+			const bool popped = (qc[3 * e + 2] & 0x8000) != 0;
+			if (popped && depth < 0) {
+				if (lane == 0) np_aheapsort(t + pl, pr - pl + 1);
+				__syncwarp();
+				continue;
+			}
+			const int pi = warp_partition(t, pl, pr, ilist, jlist);
+			--depth;
+			// numpy pushes the larger part (popped later, checks the depth) and continues with the smaller
+			int lo[2] = {pl, pi + 1}, hi[2] = {pi - 1, pr};
+			const bool left_is_pushed = !(pi - pl < pr - pi);
+			for (int k = 0; k < 2; ++k) {
+				const int sz = hi[k] - lo[k] + 1;
+				if (sz > 16) {
+					if (lane == 0) {
+						const int slot = atomicAdd(&cnt[cur ^ 1], 1);
+						const bool pushed = (k == 0) ? left_is_pushed : !left_is_pushed;
+						qn[3 * slot] = (uint16_t)lo[k];
+						qn[3 * slot + 1] = (uint16_t)hi[k];
+						qn[3 * slot + 2] = (uint16_t)((depth + 256) | (pushed ? 0x8000 : 0));
+					}
+				} else if (sz >= 2) {
+					warp_stable_small_sort(t, lo[k], hi[k]);
+				}
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) cnt[cur] = 0;
+		cur ^= 1;
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // separable 5x5 max / min on a byte image held in shared memory (words of 4 pixels).
 // OpenCV's default morphology border never wins, i.e. windows are clipped to the image.
 // ---------------------------------------------------------------------------------------------
@@ -410,6 +559,7 @@ struct MapScalars {
 	int err;
 	uint32_t rootminw;
 	uint32_t root_edge;
+	int sort_cnt[2];
 	unsigned long long sx, sy;
 	uint32_t cnt, tot;
 	uint32_t argmax_key;
@@ -446,16 +596,19 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 	__syncthreads();
 	uint32_t tma_parity = 0;
 
+	int m = -1;
 	while (true) {
-		// ---- fetch the next map ---------------------------------------------------------------
+		// ---- fetch the next map (or continue a cut-adjacent chain) ---------------------------------
 		__syncthreads();
-		if (tid == 0) {
-			const int i = atomicAdd(a.head, 1);
-			S.map_idx = (i < *a.list_len) ? a.list[i] : -1;
+		if (m < 0) {
+			if (tid == 0) {
+				const int i = atomicAdd(a.head, 1);
+				S.map_idx = (i < *a.list_len) ? a.list[i] : -1;
+			}
+			__syncthreads();
+			m = S.map_idx;
+			if (m < 0) break;
 		}
-		__syncthreads();
-		const int m = S.map_idx;
-		if (m < 0) break;
 		long long phase_t0 = clock64();
 		MapOut res;
 		res.cx = 0.0; res.cy = 0.0; res.raw_sum = 0; res.n_points = 0; res.n_clusters = -1;
@@ -593,6 +746,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 					a.out[m] = res;
 				}
 			}
+			m = -1;  // a chain continues in the next capacity class, starting with this map
 			continue;
 		}
 
@@ -758,7 +912,8 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			const int ne = n - 1;
 			for (int e = tid; e < ne; e += NT) skey[e] = (wp[e] << kKeyShift) | (uint32_t)e;
 			__syncthreads();
-			if (tid == 0) np_aquicksort(skey, ne);
+			np_aquicksort_block<NT>(skey, ne, reinterpret_cast<uint16_t *>(smem + L.a4),
+									reinterpret_cast<uint16_t *>(smem + L.a4) + L.nmax, queue, L.nmax / 6, S.sort_cnt);
 			__syncthreads();
 			for (int r = tid; r < ne; r += NT) rank[skey[r] & kKeyIdxMask] = (uint16_t)r;
 			if (tid == 0) S.root_edge = skey[ne - 1] & kKeyIdxMask;
@@ -768,20 +923,34 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			// ---- phase 4b: the dendrogram as a Cartesian tree over Prim positions --------------------
 			// Edge e joins positions e and e+1 at time rank[e]; at that time its cluster is the maximal
 			// interval around e whose edges all have smaller rank (make_single_linkage, _linkage.pyx:226).
-			for (int e = tid; e < ne; e += NT) {
-				const uint32_t re = rank[e];
-				int l = e - 1;
-				while (l >= 0 && rank[l] < re) --l;
-				int r = e + 1;
-				while (r < ne && rank[r] < re) ++r;
-				Lp1[e] = (uint16_t)(l + 1);
-				Rr[e] = (uint16_t)r;  // points L+1 .. R  (R == ne means "to the last point")
-				uint16_t par;
-				if (l < 0 && r >= ne) par = kNone16;
-				else if (l < 0) par = (uint16_t)r;
-				else if (r >= ne) par = (uint16_t)l;
-				else par = (rank[l] < rank[r]) ? (uint16_t)l : (uint16_t)r;
-				pe[e] = par;
+			{
+				uint16_t *bmax = pl;  // per-32 block maxima of rank[]; pl[] itself is written after this loop
+				for (int bb = tid; bb * 32 < ne; bb += NT) {
+					uint32_t mx = 0;
+					for (int i = bb * 32; i < min(ne, bb * 32 + 32); ++i) mx = max(mx, (uint32_t)rank[i]);
+					bmax[bb] = (uint16_t)mx;
+				}
+				__syncthreads();
+				for (int e = tid; e < ne; e += NT) {
+					const uint32_t re = rank[e];
+					int l = e - 1;
+					while (l >= 0 && rank[l] < re) {
+						if ((l & 31) == 31 && bmax[l >> 5] < re) l -= 32; else --l;
+					}
+					int r = e + 1;
+					while (r < ne && rank[r] < re) {
+						if ((r & 31) == 0 && bmax[r >> 5] < re) r += 32; else ++r;
+					}
+					if (r > ne) r = ne;
+					Lp1[e] = (uint16_t)(l + 1);
+					Rr[e] = (uint16_t)r;  // points L+1 .. R  (R == ne means "to the last point")
+					uint16_t par;
+					if (l < 0 && r >= ne) par = kNone16;
+					else if (l < 0) par = (uint16_t)r;
+					else if (r >= ne) par = (uint16_t)l;
+					else par = (rank[l] < rank[r]) ? (uint16_t)l : (uint16_t)r;
+					pe[e] = par;
+				}
 			}
 			__syncthreads();
 			// skey is dead from here: its storage becomes cL / cR
@@ -851,6 +1020,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			__syncthreads();
 			if (S.err) {
 				if (tid == 0) { res.flags |= kFlagClusterCapacity; a.out[m] = res; }
+				m = -1;
 				continue;
 			}
 
@@ -1039,6 +1209,8 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 		}
 		if (tid == 0) a.out[m] = res;
 		RVB_PHASE(10);  // results
+		// the filtered map just stored is the blend source of map m+1 (smartVidCrop.py:2369-2373)
+		m = (a.chain_next != nullptr && a.chain_next[m]) ? (m + 1) : -1;
 	}
 }
 

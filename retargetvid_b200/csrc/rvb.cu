@@ -425,7 +425,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 
 	std::vector<ClipDev> clips(nc);
 	std::vector<ShotDev> shots(NS);
-	std::vector<int> frame_shot(NF), frame_clip(NF), map_clip(NM), pred(NM, -1), store(NM, -1), depth(NM, 0);
+	std::vector<int> frame_shot(NF), frame_clip(NF), map_clip(NM), pred(NM, -1), store(NM, -1);
+	std::vector<uint8_t> chain_next(NM, 0);
 	std::vector<int> clip_final(nc * R * 3), cvrg_cfg(nc * R * 2), clip_coef(nc);
 	std::vector<FilterCoef> coefs;
 	std::vector<double> coef_fr;
@@ -469,7 +470,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 					const int src = d.map_offset + k, dst = src + 1;
 					if (store[src] < 0) store[src] = n_slots++;
 					pred[dst] = store[src];
-					depth[dst] = depth[src] + 1;
+					chain_next[src] = 1;
 				}
 			}
 		}
@@ -498,16 +499,16 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		clip_coef[i] = ci;
 	}
 	if (scratch_doubles > 0x7fffffffLL) return fail(RVB_ERR_INVALID, "batch too large (scratch)");
-	int max_depth = 0;
-	for (int v : depth) max_depth = std::max(max_depth, v);
-	const int n_waves = max_depth + 1;
-	std::vector<std::vector<int>> waves(n_waves);
-	for (int m = 0; m < NM; ++m) waves[depth[m]].push_back(m);
-
-	// counters: per wave and capacity class {head, len} of that class's work list
-	// layout of `counters`: [wave][class 0..3][2] ints
-	std::vector<int> counters(n_waves * 4 * 2, 0);
-	for (int w = 0; w < n_waves; ++w) counters[(w * 4 + 0) * 2 + 1] = (int)waves[w].size();
+	// work list: every map that does not wait for a predecessor; the starts of cut-adjacent chains come
+	// first so that the longest sequential dependencies begin as early as possible.  A chain is walked
+	// by the CTA that took its first map (chain_next), so there are no waves and no inter-CTA waits.
+	std::vector<int> work;
+	work.reserve(NM);
+	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && chain_next[m]) work.push_back(m);
+	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && !chain_next[m]) work.push_back(m);
+	// counters: per capacity class {head, len} of that class's work list
+	std::vector<int> counters(4 * 2, 0);
+	counters[1] = (int)work.size();
 
 	Staging sg;
 	const size_t o_clips = sg.add(clips.data(), clips.size() * sizeof(ClipDev));
@@ -518,18 +519,16 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_mclip = sg.add(map_clip.data(), (size_t)NM * sizeof(int));
 	const size_t o_pred = sg.add(pred.data(), (size_t)NM * sizeof(int));
 	const size_t o_store = sg.add(store.data(), (size_t)NM * sizeof(int));
+	const size_t o_chain = sg.add(chain_next.data(), (size_t)NM);
 	const size_t o_final = sg.add(clip_final.data(), clip_final.size() * sizeof(int));
 	const size_t o_cvrg = sg.add(cvrg_cfg.data(), cvrg_cfg.size() * sizeof(int));
 	const size_t o_ccoef = sg.add(clip_coef.data(), clip_coef.size() * sizeof(int));
 	const size_t o_coefs = sg.add(coefs.data(), coefs.size() * sizeof(FilterCoef));
 	const size_t o_cnt = sg.add(counters.data(), counters.size() * sizeof(int));
-	std::vector<size_t> o_wave(n_waves), o_ovf1(n_waves), o_ovf2(n_waves), o_ovf3(n_waves);
-	for (int w = 0; w < n_waves; ++w) {
-		o_wave[w] = sg.add(waves[w].data(), waves[w].size() * sizeof(int));
-		o_ovf1[w] = sg.add(nullptr, waves[w].size() * sizeof(int));
-		o_ovf2[w] = sg.add(nullptr, waves[w].size() * sizeof(int));
-		o_ovf3[w] = sg.add(nullptr, waves[w].size() * sizeof(int));
-	}
+	const size_t o_work = sg.add(work.data(), work.size() * sizeof(int));
+	const size_t o_ovf1 = sg.add(nullptr, (size_t)NM * sizeof(int));
+	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
+	const size_t o_ovf3 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_borders = sg.add(nullptr, (size_t)nc * 4 * sizeof(int));
 	const size_t o_status = sg.add(nullptr, (size_t)nc * sizeof(int));
 	const size_t o_prof = sg.add(nullptr, (size_t)nc * (H + W) * sizeof(uint32_t));
@@ -625,6 +624,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	memset(&a, 0, sizeof(a));
 	a.maps_u8 = d_u8; a.maps_f32 = d_f32; a.H = H; a.W = W; a.WPS = WPS; a.gstride = gstride;
 	a.pred = (const int *)(M + o_pred); a.store = (const int *)(M + o_store); a.map_clip = (const int *)(M + o_mclip);
+	a.chain_next = (const uint8_t *)(M + o_chain);
 	a.filt = (uint8_t *)c->filt.p; a.fstride = WPS; a.out = (MapOut *)c->mapout.p;
 	a.border_prof = nullptr;
 	a.cvrg_cfg = p->exit_on_low_cvrg ? (const int *)(M + o_cvrg) : nullptr;
@@ -634,25 +634,27 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
 	c->map_launches = 0;
 	CU(cudaEventRecord(c->ev_map0, st));
-	for (int w = 0; w < n_waves; ++w) {
-		const int nw = (int)waves[w].size();
-		int *cnt = d_cnt + (w * 4) * 2;
+	// failed / never-reached maps must not look valid
+	CU(cudaMemsetAsync(c->mapout.p, 0xFF, (size_t)NM * sizeof(MapOut), st));
+	{
+		const int nw = (int)work.size();
+		int *cnt = d_cnt;
 		// capacity classes 1024 / 2048 / 4096 / 8192 salient pixels: a map that does not fit is
 		// appended to the next class's list by the kernel itself (no host round trip)
-		a.list = (const int *)(M + o_wave[w]); a.head = cnt + 0; a.list_len = cnt + 1;
-		a.ovf_list = (int *)(M + o_ovf1[w]); a.ovf_len = cnt + 3;
+		a.list = (const int *)(M + o_work); a.head = cnt + 0; a.list_len = cnt + 1;
+		a.ovf_list = (int *)(M + o_ovf1); a.ovf_len = cnt + 3;
 		int rc = launch_map<256, 4>(c, a, H, W, WPS, occupancy_grid<256, 4>(c, make_layout(1024, H, WPS, W).total, nw));
 		if (rc) return rc;
-		a.list = (const int *)(M + o_ovf1[w]); a.head = cnt + 2; a.list_len = cnt + 3;
-		a.ovf_list = (int *)(M + o_ovf2[w]); a.ovf_len = cnt + 5;
+		a.list = (const int *)(M + o_ovf1); a.head = cnt + 2; a.list_len = cnt + 3;
+		a.ovf_list = (int *)(M + o_ovf2); a.ovf_len = cnt + 5;
 		rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W).total, nw));
 		if (rc) return rc;
-		a.list = (const int *)(M + o_ovf2[w]); a.head = cnt + 4; a.list_len = cnt + 5;
-		a.ovf_list = (int *)(M + o_ovf3[w]); a.ovf_len = cnt + 7;
+		a.list = (const int *)(M + o_ovf2); a.head = cnt + 4; a.list_len = cnt + 5;
+		a.ovf_list = (int *)(M + o_ovf3); a.ovf_len = cnt + 7;
 		rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W).total, nw));
 		if (rc) return rc;
 		// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
-		a.list = (const int *)(M + o_ovf3[w]); a.head = cnt + 6; a.list_len = cnt + 7;
+		a.list = (const int *)(M + o_ovf3); a.head = cnt + 6; a.list_len = cnt + 7;
 		a.ovf_list = nullptr; a.ovf_len = nullptr;
 		rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W).total, nw));
 		if (rc) return rc;
