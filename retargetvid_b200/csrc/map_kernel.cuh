@@ -574,8 +574,12 @@ struct MapScalars {
 		}                                                                         \
 	} while (0)
 
+// resident CTAs per SM the register budget must allow, per capacity class (shared memory bounds the same)
 template <int NT, int TPT>
-__global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
+struct MapKernelCfg { static constexpr int kMinBlocks = (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1; };
+
+template <int NT, int TPT>
+__global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_kernel(const MapArgs a) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ MapScalars S;
 	const SmemLayout &L = a.lay;
@@ -850,17 +854,17 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 			// from point 0, lowest index wins ties (np.argmin), _linkage.pyx:97-112.  Each thread keeps
 			// its TPT points in registers; key = (min reachability << 13) | index.
 			{
-				int px[TPT], py[TPT];
-				uint32_t pc[TPT], key[TPT];
+				// packed (x, y) bytes per point: |dx|,|dy| with one vabsdiffu4, dx^2+dy^2 with one dp4a
+				uint32_t pxy[TPT], pc[TPT], key[TPT];
+				const int ncnt = (n + NT - 1) / NT;  // slots that hold a point in at least one thread
 #pragma unroll
 				for (int i = 0; i < TPT; ++i) {
 					const int j = tid + i * NT;
 					if (j < n) {
-						px[i] = pts[j] & 0xFF;
-						py[i] = pts[j] >> 8;
+						pxy[i] = pts[j];
 						pc[i] = core[j];
 					} else {
-						px[i] = 0; py[i] = 0;
+						pxy[i] = 0;
 						pc[i] = kInTreeCore;
 					}
 					key[i] = 0xFFFFFFFFu;
@@ -869,18 +873,20 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 					pc[0] = kInTreeCore;  // point 0 starts the tree
 					order[0] = 0;
 				}
-				int cx = pts[0] & 0xFF, cy = pts[0] >> 8;
+				uint32_t cxy = pts[0];
 				uint32_t cc = core[0];
 				for (int step = 0; step < n - 1; ++step) {
 					uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
 					for (int i = 0; i < TPT; ++i) {
-						const int dx = px[i] - cx, dy = py[i] - cy;
-						uint32_t mr = (uint32_t)(dx * dx + dy * dy);
-						mr = max(mr, max(pc[i], cc));
-						const uint32_t k = (mr << kKeyShift) | (uint32_t)(tid + i * NT);
-						key[i] = min(key[i], k);
-						best = min(best, key[i]);
+						if (i < ncnt) {
+							const uint32_t ad = __vabsdiffu4(pxy[i], cxy);
+							const uint32_t d2 = __dp4a(ad, ad, 0u);
+							const uint32_t mr = max(d2, max(pc[i], cc));
+							const uint32_t k = (mr << kKeyShift) | (uint32_t)(tid + i * NT);
+							key[i] = min(key[i], k);
+							best = min(best, key[i]);
+						}
 					}
 					best = __reduce_min_sync(0xffffffffu, best);
 					uint32_t *wm = S.wmin[step & 1];
@@ -900,8 +906,7 @@ __global__ void __launch_bounds__(NT) map_kernel(const MapArgs a) {
 						for (int i = 0; i < TPT; ++i)
 							if (i == slot) { pc[i] = kInTreeCore; key[i] = 0xFFFFFFFFu; }
 					}
-					cx = pts[nj] & 0xFF;
-					cy = pts[nj] >> 8;
+					cxy = pts[nj];
 					cc = core[nj];
 				}
 			}

@@ -103,12 +103,13 @@ struct rvb_ctx {
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
 static const int kMaxDynSmem = 227 * 1024 - 1024;  // per-CTA opt-in limit minus the kernel's static shared memory
 
-static SmemLayout make_layout(int nmax, int H, int WPS, int W) {
+static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs) {
 	SmemLayout L;
 	memset(&L, 0, sizeof(L));
 	int o = 0;
 	L.nmax = nmax;
-	L.ncmax = std::min(nmax / 2 + 2, nmax > 4096 ? 770 : 1026);  // bounded by the 227 KB of shared memory
+	// a cluster has >= mcs points and leaf clusters are disjoint: at most 2 * nmax / mcs + 1 clusters
+	L.ncmax = std::min(2 * nmax / std::max(mcs, 2) + 3, nmax > 4096 ? 770 : nmax / 2 + 2);
 	L.pts = o; o += align_up(std::max(2 * nmax, 4 * std::max(H, W)), 16);
 	L.val = o; o += align_up(nmax, 16);
 	o = align_up(o, 128);
@@ -278,8 +279,9 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	RingTable t;
 	build_ring_table(t);
 	CU(cudaMemcpyToSymbol(c_rings, &t, sizeof(t)));
-	CU(cudaFuncSetAttribute(map_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<256, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
 	*out = c;
@@ -361,7 +363,7 @@ extern "C" int rvb_params_default(rvb_params *p, int use_best_settings) {
 // one launch of the map kernel family
 template <int NT, int TPT>
 static int launch_map(rvb_ctx *c, MapArgs a, int H, int W, int WPS, int grid) {
-	a.lay = make_layout(NT * TPT, H, WPS, W);
+	a.lay = make_layout(NT * TPT, H, WPS, W, a.mcs);
 	if (a.lay.total > (NT * TPT > 4096 ? kMaxDynSmem : 200 * 1024)) return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d needs %d B of shared memory", H, W, a.lay.total);
 	map_kernel<NT, TPT><<<grid, NT, a.lay.total, c->stream>>>(a);
 	CU(cudaGetLastError());
@@ -507,7 +509,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && chain_next[m]) work.push_back(m);
 	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && !chain_next[m]) work.push_back(m);
 	// counters: per capacity class {head, len} of that class's work list
-	std::vector<int> counters(4 * 2, 0);
+	std::vector<int> counters(5 * 2, 0);
 	counters[1] = (int)work.size();
 
 	Staging sg;
@@ -529,6 +531,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_ovf1 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf3 = sg.add(nullptr, (size_t)NM * sizeof(int));
+	const size_t o_ovf4 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_borders = sg.add(nullptr, (size_t)nc * 4 * sizeof(int));
 	const size_t o_status = sg.add(nullptr, (size_t)nc * sizeof(int));
 	const size_t o_prof = sg.add(nullptr, (size_t)nc * (H + W) * sizeof(uint32_t));
@@ -639,25 +642,26 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	{
 		const int nw = (int)work.size();
 		int *cnt = d_cnt;
-		// capacity classes 1024 / 2048 / 4096 / 8192 salient pixels: a map that does not fit is
+		// capacity classes 1536 / 2048 / 3072 / 4096 / 8192 salient pixels (shared memory per CTA grows with
+		// the capacity, so smaller classes keep more maps in flight per SM): a map that does not fit is
 		// appended to the next class's list by the kernel itself (no host round trip)
-		a.list = (const int *)(M + o_work); a.head = cnt + 0; a.list_len = cnt + 1;
-		a.ovf_list = (int *)(M + o_ovf1); a.ovf_len = cnt + 3;
-		int rc = launch_map<256, 4>(c, a, H, W, WPS, occupancy_grid<256, 4>(c, make_layout(1024, H, WPS, W).total, nw));
-		if (rc) return rc;
-		a.list = (const int *)(M + o_ovf1); a.head = cnt + 2; a.list_len = cnt + 3;
-		a.ovf_list = (int *)(M + o_ovf2); a.ovf_len = cnt + 5;
-		rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W).total, nw));
-		if (rc) return rc;
-		a.list = (const int *)(M + o_ovf2); a.head = cnt + 4; a.list_len = cnt + 5;
-		a.ovf_list = (int *)(M + o_ovf3); a.ovf_len = cnt + 7;
-		rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W).total, nw));
-		if (rc) return rc;
-		// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
-		a.list = (const int *)(M + o_ovf3); a.head = cnt + 6; a.list_len = cnt + 7;
-		a.ovf_list = nullptr; a.ovf_len = nullptr;
-		rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W).total, nw));
-		if (rc) return rc;
+		int *ovf[4] = {(int *)(M + o_ovf1), (int *)(M + o_ovf2), (int *)(M + o_ovf3), (int *)(M + o_ovf4)};
+		const int mcs = p->hdbscan_min;
+		for (int k = 0; k < 5; ++k) {
+			a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
+			a.head = cnt + 2 * k;
+			a.list_len = cnt + 2 * k + 1;
+			// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
+			a.ovf_list = (k < 4) ? ovf[k] : nullptr;
+			a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
+			int rc = RVB_OK;
+			if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs).total, nw));
+			if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs).total, nw));
+			if (k == 2) rc = launch_map<256, 12>(c, a, H, W, WPS, occupancy_grid<256, 12>(c, make_layout(3072, H, WPS, W, mcs).total, nw));
+			if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs).total, nw));
+			if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs).total, nw));
+			if (rc) return rc;
+		}
 	}
 	CU(cudaEventRecord(c->ev_map1, st));
 	c->map_timed = true;
@@ -871,8 +875,9 @@ extern "C" int rvb_debug_cluster_labels(rvb_ctx *c, const rvb_params *p, const u
 	a.t_threshold = 0; a.clust_filt = 1; a.mcs = p->hdbscan_min; a.min_samples = p->hdbscan_min_samples;
 	a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
 	int rc;
-	if (n <= 1024) rc = launch_map<256, 4>(c, a, h, w, WPS, 1);
+	if (n <= 1536) rc = launch_map<256, 6>(c, a, h, w, WPS, 1);
 	else if (n <= 2048) rc = launch_map<256, 8>(c, a, h, w, WPS, 1);
+	else if (n <= 3072) rc = launch_map<256, 12>(c, a, h, w, WPS, 1);
 	else if (n <= 4096) rc = launch_map<512, 8>(c, a, h, w, WPS, 1);
 	else rc = launch_map<512, 16>(c, a, h, w, WPS, 1);
 	if (rc) return rc;
