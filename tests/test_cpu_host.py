@@ -1,0 +1,179 @@
+"""CPU-only tests: the C ABI library loads and exports every declared symbol, host logic
+(sharding, parameter mirror, synthetic data), oracle pieces against golden vectors."""
+import os
+import re
+import statistics
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, loess_tolerance
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+	import __graft_entry__ as ge
+	ge.build()
+	from retargetvid_b200 import _cabi
+	lib = _cabi.load_library()
+	hdr = open(os.path.join(ROOT, 'include', 'retargetvid_b200.h')).read()
+	declared = set(re.findall(r'\b(rvb_[a-z_0-9]+)\s*\(', hdr))
+	assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+	for name in declared:
+		assert getattr(lib, name) is not None
+	assert b'retargetvid_b200' in lib.rvb_version()
+
+
+def test_struct_layouts_match_header_sizes():
+	"""ctypes mirrors of the ABI structs: sizes as the C compiler lays them out."""
+	from retargetvid_b200 import _cabi
+	src = '#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu", sizeof(rvb_params), sizeof(rvb_clip), sizeof(rvb_batch), sizeof(rvb_iou_batch));return 0;}' % os.path.join(ROOT, 'include', 'retargetvid_b200.h')
+	import tempfile
+	with tempfile.TemporaryDirectory() as td:
+		with open(os.path.join(td, 's.c'), 'w') as fp:
+			fp.write(src)
+		subprocess.check_call(['gcc', '-o', os.path.join(td, 's'), os.path.join(td, 's.c')])
+		out = subprocess.check_output([os.path.join(td, 's')]).decode().split()
+	import ctypes
+	got = [ctypes.sizeof(_cabi.rvb_params), ctypes.sizeof(_cabi.rvb_clip), ctypes.sizeof(_cabi.rvb_batch), ctypes.sizeof(_cabi.rvb_iou_batch)]
+	assert [int(v) for v in out] == got
+
+
+def test_product_fails_loudly_without_gpu():
+	"""No CPU fallback: without a CUDA device the context creation raises."""
+	import torch
+	if torch.cuda.is_available():
+		pytest.skip('a GPU is present')
+	from retargetvid_b200 import _cabi
+	with pytest.raises(_cabi.RvbError):
+		_cabi.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+	for dirpath, _, files in os.walk(os.path.join(ROOT, 'retargetvid_b200')):
+		for f in files:
+			if f.endswith('.py'):
+				src = open(os.path.join(dirpath, f)).read()
+				assert 'oracle' not in re.sub(r'#.*', '', src).replace('"""', ''), f
+
+
+def test_crop_params_mirror_the_reference_dict():
+	from oracle import sc_oracle
+	from retargetvid_b200 import smartVidCrop as svc
+	for best in (False, True):
+		a = svc.sc_init_crop_params(use_best_settings=best)
+		b = sc_oracle.sc_init_crop_params(use_best_settings=best)
+		assert a == b and list(a.keys()) == list(b.keys()) and len(a) == 31
+	assert svc.smart_crop_version() == '1.4.0'
+
+
+def test_lpt_sharding_balances_and_covers():
+	from retargetvid_b200 import sharding
+	rng = np.random.default_rng(0)
+	costs = [int(v) for v in rng.integers(40, 220, 200)]
+	for world in (1, 2, 4, 8):
+		shards = sharding.lpt_shards(costs, world)
+		assert sorted(sum(shards, [])) == list(range(200))
+		loads = [sum(costs[i] for i in s) for s in shards]
+		assert max(loads) - min(loads) <= max(costs)
+
+
+def test_gloo_two_ranks_shard_and_gather(tmp_path):
+	"""world_size 2 on CPU (gloo): each rank takes its LPT shard, results gathered on the host equal
+	the single-process result (the data path has no collective; the gather is host plumbing)."""
+	script = os.path.join(tmp_path, 'w.py')
+	with open(script, 'w') as fp:
+		fp.write('''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np
+import torch.distributed as dist
+from retargetvid_b200 import sharding
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+costs = [50 + (7 * i) %% 90 for i in range(23)]
+mine = sharding.my_shard(costs, rank, world)
+local = [np.full((costs[i], 4), i, dtype=np.int32) for i in mine]     # stands for the boxes of video i
+out = sharding.gather_results(local, mine, world, len(costs), dist)
+assert all(o is not None and o.shape == (costs[i], 4) and int(o[0, 0]) == i for i, o in enumerate(out))
+if rank == 0:
+	print('GATHER_OK', len(out))
+dist.destroy_process_group()
+''' % ROOT)
+	r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+						'--master-addr', '127.0.0.1', '--master-port', '29641', script], capture_output=True, text=True, timeout=300)
+	assert 'GATHER_OK 23' in r.stdout, r.stdout + r.stderr
+
+
+def test_synthetic_sampling_table_follows_the_reference_rule():
+	from retargetvid_b200 import synth
+	ti, i2o = synth.sampling_table(40, [13, 14], skip=6)
+	assert ti == [0, 6, 12, 13, 14, 20, 26, 32, 38, 39]
+	assert i2o[12] == 2 and i2o[13] == 3 and i2o[19] == 4 and i2o[39] == 9
+	vd = synth.make_clip(7, fc=40, shot_starts=[13, 14])
+	assert vd['segmentation'].tolist() == [[0, 12], [13, 13], [14, 39]]
+	assert vd['segmentation_sel'].tolist() == [[0, 2], [3, 3], [4, 9]]
+	assert vd['smaps'].shape == (140, 250, 10) and vd['smaps'].dtype == np.uint8
+
+
+def test_oracle_hdbscan_matches_library_fixture():
+	"""hdbscan_port against labels the stand-in library produced (subset; the full set runs on the GPU side)."""
+	from oracle import hdbscan_port
+	z = np.load(os.path.join(GOLDEN, 'hdbscan_fixture.npz'))
+	for i in range(0, int(z['count']), 5):
+		P = z['P_%d' % i].astype(np.int64)
+		mcs, ms = [int(v) for v in z['cfg_%d' % i]]
+		got = hdbscan_port.fit_predict(P, mcs, None if ms < 0 else ms)
+		assert np.array_equal(got, z['L_%d' % i].astype(np.int64)), i
+
+
+def test_numpy_argsort_emulation():
+	"""numpy_aquicksort == np.argsort on this box when numpy's SIMD sort is disabled (portable introsort)."""
+	code = '''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from oracle import hdbscan_port as hp
+rng = np.random.default_rng(3)
+for trial in range(120):
+	n = int(rng.integers(1, 2500))
+	v = rng.integers(1, 6, n) if trial %% 2 else np.where(rng.uniform(size=n) < 0.7, 9, rng.integers(9, 60, n))
+	assert np.array_equal(np.argsort(v.astype(np.float64)), hp.numpy_aquicksort(v)), (trial, n)
+print('SORT_OK')
+''' % ROOT
+	env = dict(os.environ)
+	env['NPY_DISABLE_CPU_FEATURES'] = ('AVX512F AVX512CD AVX512_KNL AVX512_KNM AVX512_SKX AVX512_CLX AVX512_CNL '
+									'AVX512_ICL AVX512_SPR AVX2')
+	r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+	assert 'SORT_OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_oracle_pyloess_and_eval_golden():
+	from oracle import eval_oracle, sc_oracle
+	z = np.load(os.path.join(GOLDEN, 'loess_fixture.npz'))
+	xx, yy = z['xx'], z['yy']
+	n_xx = (xx - xx.min()) / (xx.max() - xx.min())
+	n_yy = (yy - yy.min()) / (yy.max() - yy.min())
+	for deg, key in ((1, 'main_deg1_w7'), (2, 'main_deg2_w7')):
+		got = [sc_oracle.loess_estimate(n_xx, n_yy, yy.min(), yy.max(), xx.min(), xx.max(), x, 7, deg) for x in xx]
+		assert np.allclose(got, z[key], rtol=0, atol=1e-9)
+	for cl in (12, 60, 300):
+		got = sc_oracle.loess_handler(np.arange(cl), z['y_%d' % cl], 1, int(z['w_%d' % cl]), 2)
+		# the reference's pinv of the uncentred normal equations is itself only reproducible to this level
+		# across BLAS/SIMD code paths (the fixture was generated with numpy's SIMD dispatch off)
+		assert np.max(np.abs(np.array(got) - z['est_%d' % cl])) <= loess_tolerance(cl)
+	# evaluator golden on the first 25 videos, 1-3, annotator 1
+	e = np.load(os.path.join(GOLDEN, 'eval_fixture.npz'))
+	lens = e['annot_len_1_1-3']
+	offs = np.concatenate([[0], np.cumsum(lens)])
+	ml = e['method_len_1-3']
+	moffs = np.concatenate([[0], np.cumsum(ml)])
+	vals = []
+	for i in range(25):
+		a = e['annot_1_1-3'][offs[i]:offs[i + 1]].astype(int).tolist()
+		m = e['method_1-3'][moffs[i]:moffs[i + 1]].astype(int).tolist()
+		vals.append(eval_oracle.video_iou(m, a, len(a)))
+	assert all(0.0 <= v <= 1.0 for v in vals) and abs(statistics.mean(vals) - 0.5) < 0.25

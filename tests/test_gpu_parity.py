@@ -236,3 +236,145 @@ def test_error_behaviour(engine):
 	with pytest.raises(NotImplementedError):
 		svc.smart_vid_crop('x.mp4', svc.sc_init_crop_params(use_best_settings=True), save_vid=False,
 						vid_data=synth.make_clip(3, fc=30))
+
+
+def _run_raw(engine, vds, CP, ratios, maps_kind, maps_arrays):
+	"""Direct C-ABI call with an explicit map layout (host memory)."""
+	import ctypes as C
+	from retargetvid_b200 import _cabi
+	nc = len(vds)
+	clips = (_cabi.rvb_clip * nc)()
+	shots, tinds = [], []
+	mo = fo = so = 0
+	ptrs = (C.c_void_p * nc)()
+	for i, vd in enumerate(vds):
+		c = clips[i]
+		c.n_maps, c.n_frames, c.n_shots = vd['fc_sel'], vd['fc'], len(vd['segmentation'])
+		c.h_orig, c.w_orig, c.fr = vd['h_orig'], vd['w_orig'], vd['fr']
+		c.map_offset, c.frame_offset, c.shot_offset = mo, fo, so
+		shots.append(np.concatenate([vd['segmentation'], vd['segmentation_sel']], axis=1))
+		tinds.append(np.asarray(vd['true_inds'], dtype=np.int32))
+		ptrs[i] = maps_arrays[i].ctypes.data
+		mo += c.n_maps
+		fo += c.n_frames
+		so += c.n_shots
+	shots = np.ascontiguousarray(np.concatenate(shots), dtype=np.int32)
+	tinds = np.ascontiguousarray(np.concatenate(tinds), dtype=np.int32)
+	b = _cabi.rvb_batch()
+	b.n_clips, b.h_process, b.w_process, b.n_ratios = nc, vds[0]['h_process'], vds[0]['w_process'], len(ratios)
+	b.maps_kind, b.mem_space = maps_kind, _cabi.RVB_MEM_HOST
+	b.row_stride = maps_arrays[0].shape[-1] if maps_kind == _cabi.RVB_MAPS_U8_NHW else 0
+	for r, s in enumerate(ratios):
+		a, bb = s.split(':')
+		b.ratio_w[r], b.ratio_h[r] = float(a), float(bb)
+	b.clips = clips
+	b.shots = shots.ctypes.data
+	b.true_inds = tinds.ctypes.data
+	b.clip_maps = ptrs
+	boxes = np.empty((len(ratios), fo, 4), dtype=np.int32)
+	filt = np.empty((mo, b.h_process, b.w_process), dtype=np.uint8)
+	b.boxes = boxes.ctypes.data
+	b.filtered_maps = filt.ctypes.data
+	b.row_stride_out = b.w_process
+	engine.ctx.crop_track_batch(_cabi.params_from_crop_params(CP), b)
+	return boxes, filt
+
+
+def test_map_layouts_agree(engine):
+	"""reference layout [H,W,N], device-native [N,H,256] and float32 log-saliency entries."""
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vds = [synth.make_clip(700 + i, fc=90, shot_starts=[45] if i else [], keep_logp=True) for i in range(3)]
+	CP = svc.sc_init_crop_params()
+	ratios = ['1:3', '9:16']
+	hwn = [np.ascontiguousarray(vd['smaps']) for vd in vds]
+	b0, f0 = _run_raw(engine, vds, CP, ratios, _cabi.RVB_MAPS_U8_HWN, hwn)
+	nhw = []
+	for vd in vds:
+		a = np.zeros((vd['fc_sel'], 140, 256), dtype=np.uint8)
+		a[:, :, :250] = np.transpose(vd['smaps'], (2, 0, 1))
+		a[:, :, 250:] = 77   # padding bytes are the caller's garbage and must be ignored
+		nhw.append(a)
+	b1, f1 = _run_raw(engine, vds, CP, ratios, _cabi.RVB_MAPS_U8_NHW, nhw)
+	assert np.array_equal(b0, b1) and np.array_equal(f0, f1)
+
+
+def test_float32_entry(engine):
+	"""a1 (unisal/train.py:1270-1274) fused in front of the path: the uint8 quantisation may differ from
+	numpy's by one grey level only where v*255 is within float32 rounding of an integer (CUDA rounds exp
+	correctly, numpy/torch do not); such pixels are enumerated and must be rare."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vd = synth.make_clip(811, fc=60, keep_logp=True)
+	logp = np.ascontiguousarray(vd['_logp'], dtype=np.float32)
+	CP = svc.sc_init_crop_params()
+	CP['clust_filt'] = False
+	CP['t_threshold'] = 0       # filtered map == quantised map
+	_, q = _run_raw(engine, [vd], CP, ['1:3'], _cabi.RVB_MAPS_F32_NHW, [logp])
+	want = np.stack([sc_oracle.normalise_u8(logp[i]) for i in range(logp.shape[0])])
+	diff = q.astype(int) - want.astype(int)
+	assert np.max(np.abs(diff)) <= 1
+	flips = np.argwhere(diff != 0)
+	assert len(flips) <= q.size // 20000, len(flips)
+	for (i, y, x) in flips:
+		e = np.exp(logp[i].astype(np.float64))
+		v = e[y, x] / e.max() * 255.0
+		assert abs(v - round(v)) < 1e-4, (i, y, x, v)
+	# and the full path from float32 maps equals the path from the quantised maps it produced
+	CP = svc.sc_init_crop_params()
+	b_f32, _ = _run_raw(engine, [vd], CP, ['1:3'], _cabi.RVB_MAPS_F32_NHW, [logp])
+	vd_q = dict(vd)
+	vd_q['smaps'] = np.ascontiguousarray(np.transpose(q, (1, 2, 0)))
+	b_u8, _ = _run_raw(engine, [vd_q], CP, ['1:3'], _cabi.RVB_MAPS_U8_HWN, [vd_q['smaps']])
+	assert np.array_equal(b_f32, b_u8)
+
+
+def test_full_size_properties(engine):
+	"""BASELINE configs[2] size (200 clips x 2 ratios): size-independent properties of the output."""
+	import bench
+	from retargetvid_b200 import smartVidCrop as svc
+	vds = bench.make_workload(200, 0)
+	CP = svc.sc_init_crop_params()
+	res = engine.run(vds, CP, ['1:3', '3:1'], detail=True)
+	rng = np.random.default_rng(0)
+	for i, (vd, r) in enumerate(zip(vds, res)):
+		assert r.status == 0
+		b13, b31 = r.boxes[0], r.boxes[1]
+		# crop size and containment (sc_compute_bb's clamps): 120x360 and 640x213 inside 640x360
+		assert np.all(b13[:, 2] - b13[:, 0] == 120) and np.all(b13[:, 1] == 0) and np.all(b13[:, 3] == 360)
+		assert np.all(b31[:, 3] - b31[:, 1] == 213) and np.all(b31[:, 0] == 0) and np.all(b31[:, 2] == 640)
+		assert b13[:, 0].min() >= 0 and b13[:, 2].max() <= 640 and b31[:, 1].min() >= 0 and b31[:, 3].max() <= 360
+		# both ratios come from the same centre track
+		cx = (r.series[4] / (250.0 / 640.0)).astype(np.int64)
+		assert np.array_equal(np.clip(cx - 60, 0, 520), b13[:, 0])
+		# centres lie inside the map, kept pixels never exceed the thresholded pixels by more than closing can add
+		assert np.all((r.dx >= 0) & (r.dx <= 249) & (r.dy >= 0) & (r.dy <= 139))
+	# a random subset recomputed alone gives bit-identical results (batch independence, no cross-clip state)
+	for i in rng.choice(len(vds), 6, replace=False):
+		one = engine.run([vds[i]], CP, ['1:3', '3:1'], detail=True)[0]
+		assert np.array_equal(one.boxes, res[i].boxes) and np.array_equal(one.series, res[i].series)
+	# idempotence of the filter: feeding the filtered maps back leaves them unchanged when no blend applies
+	vd = dict(vds[3])
+	first = engine.run([vd], CP, ['1:3'], detail=True, want_filtered=True)[0]
+	vd2 = dict(vd)
+	vd2['smaps'] = np.ascontiguousarray(np.transpose(first.filtered, (1, 2, 0)))
+	again = engine.run([vd2], CP, ['1:3'], detail=True, want_filtered=True)[0]
+	seg_cuts = set(int(s[0]) for s in vd['segmentation_sel'])
+	free = [k for k in range(3, vd['fc_sel']) if not ({k - 2, k - 1, k} & seg_cuts)]
+	kept = (first.filtered[free] > 0).sum()
+	assert (again.filtered[free] > 0).sum() <= kept * 1.05 + 5
+
+
+def test_iou_properties_full_size(engine):
+	"""config 2 size: IoU(a, a) == 1 for every frame, symmetry, and a checksum of the per-video sums."""
+	from retargetvid_b200 import retargetvid_eval as rev
+	method, annots, frame_counts, _ = _eval_fixture()
+	ann = [a['3-1'] for a in annots]
+	self_iou, _, _ = rev.evaluate_arrays(engine.ctx, annots[0]['3-1'], [annots[0]['3-1']], frame_counts)
+	assert all(v[0] == 1.0 for v in self_iou)
+	ab, _, _ = rev.evaluate_arrays(engine.ctx, annots[1]['3-1'], [annots[2]['3-1']], frame_counts)
+	ba, _, _ = rev.evaluate_arrays(engine.ctx, annots[2]['3-1'], [annots[1]['3-1']], frame_counts)
+	assert ab == ba
