@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			uint32_t total;
 			uint32_t base = block_excl_scan<NT>(c, S.red, total);
 			n = (int)total;
-			if (n <= L.nmax) {
+			if (a.clust_filt && n <= L.nmax) {
 				for (int i = w0; i < w1; ++i) {
 					uint32_t v = map32[i];
 					if (v == 0u) continue;
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 		res.n_points = n;
 		__syncthreads();
 		RVB_PHASE(1);  // threshold + compaction
-		if (n > L.nmax) {
+		if (a.clust_filt && n > L.nmax) {
 			// does not fit this launch's capacity: hand it to the next size class
 			if (tid == 0) {
 				if (a.ovf_list != nullptr) {
