@@ -168,11 +168,15 @@ def gpu_arm(args, rank, world, local_rank):
 	NF = sum(v['fc'] for v in vds)
 	NS = sum(len(v['segmentation']) for v in vds)
 
-	ctx = _cabi.Context(local_rank)
-	# a real (non-default) stream shared by torch and the library, so that torch's CUDA events bracket the library's work
-	stream = torch.cuda.Stream()
-	torch.cuda.set_stream(stream)
-	ctx.set_stream(stream.cuda_stream)
+	# NCTX contexts, each with its own stream and workspace: consecutive batches are independent, so
+	# they are pipelined (the latency tail of one batch's few very large maps overlaps the next batch)
+	NCTX = max(1, args.streams)
+	ctxs = [_cabi.Context(local_rank) for _ in range(NCTX)]
+	streams = [torch.cuda.Stream() for _ in range(NCTX)]
+	for cx, st in zip(ctxs, streams):
+		cx.set_stream(st.cuda_stream)
+	ctx = ctxs[0]
+	torch.cuda.set_stream(streams[0])
 	CP = svc.sc_init_crop_params()
 	params = _cabi.params_from_crop_params(CP)
 
@@ -203,7 +207,8 @@ def gpu_arm(args, rank, world, local_rank):
 		hm[off:off + n] = vd['smaps'].reshape(-1)
 		ptrs[i] = host_maps.data_ptr() + off
 		off += n
-	host_boxes = torch.empty((R, NF, 4), dtype=torch.int32).pin_memory()
+	host_boxes_all = [torch.empty((R, NF, 4), dtype=torch.int32).pin_memory() for _ in range(NCTX)]
+	host_boxes = host_boxes_all[0]
 
 	# device-resident input: device-native layout uint8 [N][H][256]
 	dev_maps = torch.zeros((NM, H, WPS), dtype=torch.uint8, device='cuda')
@@ -212,10 +217,11 @@ def gpu_arm(args, rank, world, local_rank):
 		n = vd['fc_sel']
 		dev_maps[mo:mo + n, :, :W] = torch.from_numpy(np.ascontiguousarray(np.transpose(vd['smaps'], (2, 0, 1)))).cuda()
 		mo += n
-	dev_boxes = torch.empty((R, NF, 4), dtype=torch.int32, device='cuda')
+	dev_boxes_all = [torch.empty((R, NF, 4), dtype=torch.int32, device='cuda') for _ in range(NCTX)]
+	dev_boxes = dev_boxes_all[0]
 	torch.cuda.synchronize()
 
-	def batch(device_resident):
+	def batch(device_resident, k=0):
 		b = _cabi.rvb_batch()
 		b.n_clips, b.h_process, b.w_process, b.n_ratios = nc, H, W, R
 		for r, s in enumerate(RATIOS):
@@ -227,59 +233,108 @@ def gpu_arm(args, rank, world, local_rank):
 		if device_resident:
 			b.maps_kind, b.mem_space, b.row_stride = _cabi.RVB_MAPS_U8_NHW, _cabi.RVB_MEM_DEVICE, WPS
 			b.maps = dev_maps.data_ptr()
-			b.boxes = dev_boxes.data_ptr()
+			b.boxes = dev_boxes_all[k].data_ptr()
 		else:
 			b.maps_kind, b.mem_space = _cabi.RVB_MAPS_U8_HWN, _cabi.RVB_MEM_HOST
 			b.maps = None
 			b.clip_maps = ptrs
-			b.boxes = host_boxes.data_ptr()
+			b.boxes = host_boxes_all[k].data_ptr()
 		return b
 
-	b_dev, b_host = batch(True), batch(False)
+	b_devs = [batch(True, k) for k in range(NCTX)]
+	b_hosts = [batch(False, k) for k in range(NCTX)]
+	b_dev, b_host = b_devs[0], b_hosts[0]
 
 	def barrier():
 		if dist is not None:
 			dist.barrier()
 		torch.cuda.synchronize()
 
-	def timed(b, steps, collect_map_ms=False):
-		barrier()
-		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		l0 = ctx.launch_count()
-		map_ms, map_launches = 0.0, 0
-		e0.record()
-		for _ in range(steps):
-			ctx.crop_track_batch(params, b)
-			if collect_map_ms:
-				ms, nl = ctx.last_map_kernel_ms()   # waits for this step's map kernels only
-				map_ms += ms
-				map_launches += nl
-		e1.record()
-		barrier()
-		ms = e0.elapsed_time(e1)
+	def reduce_max(ms):
 		if dist is not None:
 			t = torch.tensor([ms], device='cuda', dtype=torch.float64)
 			dist.all_reduce(t, op=dist.ReduceOp.MAX)
 			ms = float(t.item())
-		return ms, ctx.launch_count() - l0, map_ms, map_launches
+		return ms
+
+	def launches():
+		return sum(cx.launch_count() for cx in ctxs)
+
+	def timed_device(steps):
+		"""device-resident, asynchronous calls round-robin over the contexts; CUDA events on stream 0
+		bracket all streams (they wait for the start event, stream 0 waits for their end events)."""
+		barrier()
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		l0 = launches()
+		e0.record(streams[0])
+		for st in streams[1:]:
+			st.wait_event(e0)
+		for k in range(steps):
+			ctxs[k % NCTX].crop_track_batch(params, b_devs[k % NCTX])
+		for st in streams[1:]:
+			ev = torch.cuda.Event()
+			ev.record(st)
+			streams[0].wait_event(ev)
+		e1.record(streams[0])
+		barrier()
+		return reduce_max(e0.elapsed_time(e1)), launches() - l0
+
+	def timed_host(steps):
+		"""end to end: synchronous host-buffer calls, one host thread per context."""
+		barrier()
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		errs = []
+
+		def worker(k):
+			try:
+				for i in range(k, steps, NCTX):
+					ctxs[k].crop_track_batch(params, b_hosts[k])
+			except Exception as e:  # pragma: no cover
+				errs.append(e)
+		e0.record(streams[0])
+		ths = [threading.Thread(target=worker, args=(k,)) for k in range(NCTX)]
+		for t in ths:
+			t.start()
+		for t in ths:
+			t.join()
+		e1.record(streams[0])
+		barrier()
+		if errs:
+			raise errs[0]
+		return reduce_max(e0.elapsed_time(e1))
+
+	def timed_map_kernel(steps):
+		"""the dominant kernel alone: one context, its own CUDA events around the map-kernel launches"""
+		barrier()
+		map_ms, map_launches = 0.0, 0
+		for _ in range(steps):
+			ctx.crop_track_batch(params, b_dev)
+			ms, nl = ctx.last_map_kernel_ms()
+			map_ms += ms
+			map_launches += nl
+		barrier()
+		return map_ms, map_launches
 
 	for _ in range(args.warmup):
-		ctx.crop_track_batch(params, b_dev)
+		for k in range(NCTX):
+			ctxs[k].crop_track_batch(params, b_devs[k])
 	for _ in range(max(1, args.warmup // 2)):
-		ctx.crop_track_batch(params, b_host)
+		for k in range(NCTX):
+			ctxs[k].crop_track_batch(params, b_hosts[k])
 	torch.cuda.synchronize()
 	first_boxes = dev_boxes.cpu().numpy().copy()
-	assert np.array_equal(first_boxes, host_boxes.numpy()), 'device-resident and host-buffer paths disagree'
+	for k in range(NCTX):
+		assert np.array_equal(first_boxes, host_boxes_all[k].numpy()), 'device-resident and host-buffer paths disagree'
+		assert np.array_equal(first_boxes, dev_boxes_all[k].cpu().numpy())
 
 	sampler = ClockSampler(local_rank)
 	if rank == 0:
 		sampler.start()
-	ms_dev, launches, _, _ = timed(b_dev, args.steps)
-	ms_e2e, _, _, _ = timed(b_host, args.steps)
+	ms_dev, launches_n = timed_device(args.steps)
+	ms_e2e = timed_host(args.steps)
 	clocks = sampler.stop() if rank == 0 else None
-	# roofline of the dominant kernel (the fused map kernel family): its own CUDA events, separate
-	# pass so that waiting on the events does not perturb the throughput numbers above
-	_, _, map_ms, map_launches = timed(b_dev, args.steps, collect_map_ms=True)
+	# roofline of the dominant kernel (the fused map kernel family): separate un-pipelined pass
+	map_ms, map_launches = timed_map_kernel(args.steps)
 
 	if args.phases and rank == 0:
 		ctx.phase_cycles(True)
@@ -320,10 +375,11 @@ def gpu_arm(args, rank, world, local_rank):
 					'clips_per_gpu': nc, 'frames_per_gpu': NF, 'maps_per_gpu': NM, 'ratios': RATIOS,
 					'maps_per_sec': world * NM * args.steps / (ms_dev / 1e3),
 					'input_bytes_per_gpu': NM * H * WPS, 'l2': 'inputs larger than L2 (no flush needed)',
-					'value_entry': 'device-resident uint8 [N][140][256]', 'e2e_entry': 'pinned host uint8 [H][W][N] per clip'},
+					'value_entry': 'device-resident uint8 [N][140][256]', 'e2e_entry': 'pinned host uint8 [H][W][N] per clip',
+					'batches_in_flight': NCTX},
 			'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(NM * H * W), 'd2h_bytes_per_step': int(R * NF * 16),
 					'ms_per_step': ms_e2e / args.steps},
-			'gpu_launches': int(launches),
+			'gpu_launches': int(launches_n),
 			'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
 						'traffic': traffic, 'kernel': 'rvb::map_kernel<NT,TPT> (all capacity classes and waves of a step)',
 						'algorithmic_bytes_per_step': algo, 'kernel_ms_per_step': map_ms / args.steps,
@@ -336,7 +392,8 @@ def gpu_arm(args, rank, world, local_rank):
 	if dist is not None:
 		dist.barrier()
 		dist.destroy_process_group()
-	ctx.close()
+	for cx in ctxs:
+		cx.close()
 	return line
 
 
@@ -367,6 +424,7 @@ def main():
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--clips', type=int, default=200, help='clips per GPU (BASELINE configs[2]: 200)')
 	ap.add_argument('--cpu-sample', type=int, default=16, help='clips in the bounded CPU sample')
+	ap.add_argument('--streams', type=int, default=2, help='contexts/streams used to pipeline consecutive batches')
 	ap.add_argument('--phases', action='store_true', help='also print the per-phase SM-cycle split of the map kernel (stderr)')
 	args = ap.parse_args()
 	rank = int(os.environ.get('RANK', '0'))
