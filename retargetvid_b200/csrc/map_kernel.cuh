@@ -574,6 +574,83 @@ struct MapScalars {
 		}                                                                         \
 	} while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Prim on the mutual-reachability graph, all pairs, K points per thread in registers (K is the exact
+// number of occupied slots, so the unrolled update carries no per-slot predicate).  From point 0,
+// lowest index wins ties (np.argmin) -- _linkage.pyx:97-112.  key = (min reachability << 13) | index;
+// |dx|,|dy| by one VABSDIFF4, dx^2+dy^2 by one IDP.4A, max(d2, core_j, core_u) by one VIMNMX3.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int K>
+__device__ __forceinline__ void prim_all_pairs(const uint16_t *pts, const uint32_t *core, uint16_t *order, uint32_t *wp,
+												uint32_t (*wmin)[32], int n) {
+	constexpr int NW = NT / 32;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint32_t pxy[K], pc[K], key[K], idc[K];
+#pragma unroll
+	for (int i = 0; i < K; ++i) {
+		const int j = tid + i * NT;
+		idc[i] = (uint32_t)j;
+		if (j < n) {
+			pxy[i] = pts[j];
+			pc[i] = core[j];
+		} else {
+			pxy[i] = 0;
+			pc[i] = kInTreeCore;
+		}
+		key[i] = 0xFFFFFFFFu;
+	}
+	if (tid == 0) {
+		pc[0] = kInTreeCore;  // point 0 starts the tree
+		order[0] = 0;
+	}
+	uint32_t cxy = pts[0];
+	uint32_t cc = core[0];
+	for (int step = 0; step < n - 1; ++step) {
+		uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+		for (int i = 0; i < K; ++i) {
+			const uint32_t ad = __vabsdiffu4(pxy[i], cxy);
+			const uint32_t d2 = __dp4a(ad, ad, 0u);
+			const uint32_t mr = max(d2, max(pc[i], cc));
+			uint32_t k;
+			asm("mad.lo.u32 %0, %1, 8192, %2;" : "=r"(k) : "r"(mr), "r"(idc[i]));
+			key[i] = min(key[i], k);
+			best = min(best, key[i]);
+		}
+		best = __reduce_min_sync(0xffffffffu, best);
+		uint32_t *wm = wmin[step & 1];
+		if (lane == 0) wm[warp] = best;
+		__syncthreads();
+		uint32_t g = (lane < NW) ? wm[lane] : 0xFFFFFFFFu;
+		g = __reduce_min_sync(0xffffffffu, g);
+		const int nj = (int)(g & kKeyIdxMask);
+		if (tid == 0) {
+			order[step + 1] = (uint16_t)nj;
+			wp[step] = g >> kKeyShift;
+		}
+		// the owner retires the new node
+		if ((nj % NT) == tid) {
+			const int slot = nj / NT;
+#pragma unroll
+			for (int i = 0; i < K; ++i)
+				if (i == slot) { pc[i] = kInTreeCore; key[i] = 0xFFFFFFFFu; }
+		}
+		cxy = pts[nj];
+		cc = core[nj];
+	}
+}
+
+template <int NT, int TPT, int K = 1>
+__device__ __forceinline__ void prim_dispatch(int ncnt, const uint16_t *pts, const uint32_t *core, uint16_t *order,
+											   uint32_t *wp, uint32_t (*wmin)[32], int n) {
+	if constexpr (K >= TPT) {
+		prim_all_pairs<NT, TPT>(pts, core, order, wp, wmin, n);
+	} else {
+		if (ncnt <= K) prim_all_pairs<NT, K>(pts, core, order, wp, wmin, n);
+		else prim_dispatch<NT, TPT, K + 1>(ncnt, pts, core, order, wp, wmin, n);
+	}
+}
+
 // resident CTAs per SM the register budget must allow, per capacity class (shared memory bounds the same)
 template <int NT, int TPT>
 struct MapKernelCfg { static constexpr int kMinBlocks = (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1; };
@@ -851,65 +928,9 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 
 			RVB_PHASE(2);  // core distances
 			// ---- phase 3: Prim on the mutual-reachability graph -------------------------------------
-			// from point 0, lowest index wins ties (np.argmin), _linkage.pyx:97-112.  Each thread keeps
-			// its TPT points in registers; key = (min reachability << 13) | index.
-			{
-				// packed (x, y) bytes per point: |dx|,|dy| with one vabsdiffu4, dx^2+dy^2 with one dp4a
-				uint32_t pxy[TPT], pc[TPT], key[TPT];
-				const int ncnt = (n + NT - 1) / NT;  // slots that hold a point in at least one thread
-#pragma unroll
-				for (int i = 0; i < TPT; ++i) {
-					const int j = tid + i * NT;
-					if (j < n) {
-						pxy[i] = pts[j];
-						pc[i] = core[j];
-					} else {
-						pxy[i] = 0;
-						pc[i] = kInTreeCore;
-					}
-					key[i] = 0xFFFFFFFFu;
-				}
-				if (tid == 0) {
-					pc[0] = kInTreeCore;  // point 0 starts the tree
-					order[0] = 0;
-				}
-				uint32_t cxy = pts[0];
-				uint32_t cc = core[0];
-				for (int step = 0; step < n - 1; ++step) {
-					uint32_t best = 0xFFFFFFFFu;
-#pragma unroll
-					for (int i = 0; i < TPT; ++i) {
-						if (i < ncnt) {
-							const uint32_t ad = __vabsdiffu4(pxy[i], cxy);
-							const uint32_t d2 = __dp4a(ad, ad, 0u);
-							const uint32_t mr = max(d2, max(pc[i], cc));
-							const uint32_t k = (mr << kKeyShift) | (uint32_t)(tid + i * NT);
-							key[i] = min(key[i], k);
-							best = min(best, key[i]);
-						}
-					}
-					best = __reduce_min_sync(0xffffffffu, best);
-					uint32_t *wm = S.wmin[step & 1];
-					if (lane == 0) wm[warp] = best;
-					__syncthreads();
-					uint32_t g = (lane < NW) ? wm[lane] : 0xFFFFFFFFu;
-					g = __reduce_min_sync(0xffffffffu, g);
-					const int nj = (int)(g & kKeyIdxMask);
-					if (tid == 0) {
-						order[step + 1] = (uint16_t)nj;
-						wp[step] = g >> kKeyShift;
-					}
-					// the owner retires the new node
-					if ((nj % NT) == tid) {
-						const int slot = nj / NT;
-#pragma unroll
-						for (int i = 0; i < TPT; ++i)
-							if (i == slot) { pc[i] = kInTreeCore; key[i] = 0xFFFFFFFFu; }
-					}
-					cxy = pts[nj];
-					cc = core[nj];
-				}
-			}
+			// (prim_all_pairs above; specialised on the number of occupied register slots)
+			static_assert(kKeyShift == 13, "prim_all_pairs multiplies by 8192");
+			prim_dispatch<NT, TPT>((n + NT - 1) / NT, pts, core, order, wp, S.wmin, n);
 			__syncthreads();
 
 			RVB_PHASE(3);  // Prim
