@@ -424,7 +424,7 @@ def main():
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--clips', type=int, default=200, help='clips per GPU (BASELINE configs[2]: 200)')
 	ap.add_argument('--cpu-sample', type=int, default=16, help='clips in the bounded CPU sample')
-	ap.add_argument('--streams', type=int, default=2, help='contexts/streams used to pipeline consecutive batches')
+	ap.add_argument('--streams', type=int, default=3, help='contexts/streams used to pipeline consecutive batches')
 	ap.add_argument('--phases', action='store_true', help='also print the per-phase SM-cycle split of the map kernel (stderr)')
 	args = ap.parse_args()
 	rank = int(os.environ.get('RANK', '0'))

@@ -378,3 +378,36 @@ def test_iou_properties_full_size(engine):
 	ab, _, _ = rev.evaluate_arrays(engine.ctx, annots[1]['3-1'], [annots[2]['3-1']], frame_counts)
 	ba, _, _ = rev.evaluate_arrays(engine.ctx, annots[2]['3-1'], [annots[1]['3-1']], frame_counts)
 	assert ab == ba
+
+
+def test_coverage_score_crop_window_and_padding_fallback(engine):
+	"""a7 with the Appendix B-1 window (config 4: 1080p, multi-shot, 9:16, padding fallback enabled):
+	scores equal the oracle's restatement of smartVidCrop.py:1310-1331 bit for bit; the reference window
+	reproduces its 0.0; a low score makes smart_vid_crop return result='padded' without boxes."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vd = synth.make_clip(4001, fc=150, w_orig=1920, h_orig=1080, shot_starts=[70, 76])
+	CP = svc.sc_init_crop_params()
+	CP['exit_on_low_cvrg'] = True
+	ratios = ['9:16', '3:1', '16:9']
+	res = engine.run([vd], CP, ratios, detail=True, want_filtered=True, cvrg_window='crop')[0]
+	filt = np.ascontiguousarray(np.transpose(res.filtered, (1, 2, 0)))
+	for k, r in enumerate(ratios):
+		mode, wf, hf = sc_oracle.sc_calc_dest_size(vd['w_orig'], vd['h_orig'], r)
+		want, per_map = sc_oracle.sc_compute_cvrg_score(filt, mode, vd['w_process'], vd['h_process'], 'crop',
+														wf, hf, vd['w_orig'], vd['h_orig'])
+		assert float(res.cvrg_scores[k]) == want, (r, float(res.cvrg_scores[k]), want)
+	ref0 = engine.run([vd], CP, ratios, detail=True, cvrg_window='reference')[0]
+	assert list(ref0.cvrg_scores) == [0.0, 0.0, 0.0]
+	# the whole oracle pipeline on this clip (shots of 6 and 74 frames, LOESS on)
+	CP2 = dict(CP)
+	CP2['out_ratio'] = '9:16'
+	want = sc_oracle.smart_vid_crop_oracle(vd, CP2, cvrg_window='crop')
+	assert np.array_equal(filt, want['smaps_filtered'])
+	assert np.array_equal(res.boxes[0], np.array(want['bbs'], dtype=np.int32))
+	# padding fallback: a coverage score can never reach t_cvrg=1.01
+	CP3 = dict(CP2)
+	CP3['t_cvrg'] = 1.01
+	VD, info = svc.smart_vid_crop('c4.mp4', CP3, save_vid=False, vid_data=dict(vd), cvrg_window='crop')
+	assert info['result'] == 'padded' and 'bbs' not in VD and info['coverage_score'] == want['mean_cvrg_score']
