@@ -1,0 +1,61 @@
+"""ORACLE (test infrastructure).  numpy restatement of the two cv2.resize calls on the hot path
+(smartVidCrop.py:1078-1084, 1158, 1184) for uint8 single-channel images: INTER_LINEAR (OpenCV
+modules/imgproc/src/resize.cpp: float32 source coordinate, weights rounded to 1/2048, horizontal pass
+in int, vertical pass ((b*(S>>4))>>16, +2, >>2) with clipped rows) and INTER_NEAREST.  Checked against
+cv2 itself in tests/test_cpu_host.py.  Exact 2x down-scaling is not covered (OpenCV switches INTER_LINEAR to
+INTER_AREA there); neither preset uses it."""
+import numpy as np
+
+
+def cv_round(v):
+	return int(np.rint(v))  # cvRound: round half to even
+
+
+def _linear_coeffs(dsize, ssize, scale, vertical):
+	idx = np.zeros(dsize, dtype=np.int64)
+	a0 = np.zeros(dsize, dtype=np.int64)
+	a1 = np.zeros(dsize, dtype=np.int64)
+	for d in range(dsize):
+		f = np.float32((d + 0.5) * scale - 0.5)
+		s = int(np.floor(f))
+		f = np.float32(f - np.float32(s))
+		if not vertical:
+			if s < 0:
+				s, f = 0, np.float32(0)
+			if s >= ssize - 1:
+				s, f = ssize - 1, np.float32(0)
+		idx[d] = s
+		a0[d] = cv_round(np.float32(np.float32(1.0) - f) * np.float32(2048))
+		a1[d] = cv_round(f * np.float32(2048))
+	return idx, a0, a1
+
+
+def down_size(n, factor):
+	"""dsize of cv2.resize(src, None, fx=1/factor): saturate_cast<int>(n * fx)"""
+	return cv_round(n * (1.0 / factor))
+
+
+def resize_linear_u8(src, dsize_wh=None, fx=None, fy=None):
+	H, W = src.shape
+	if dsize_wh is None:
+		dw, dh = cv_round(W * fx), cv_round(H * fy)
+		sx, sy = 1.0 / fx, 1.0 / fy
+	else:
+		dw, dh = dsize_wh
+		sx, sy = 1.0 / (dw / W), 1.0 / (dh / H)
+	xi, xa0, xa1 = _linear_coeffs(dw, W, sx, False)
+	yi, yb0, yb1 = _linear_coeffs(dh, H, sy, True)
+	s = src.astype(np.int64)
+	rows = s[:, xi] * xa0[None, :] + s[:, np.minimum(xi + 1, W - 1)] * xa1[None, :]
+	y0 = np.clip(yi, 0, H - 1)
+	y1 = np.clip(yi + 1, 0, H - 1)
+	out = (((yb0[:, None] * (rows[y0, :] >> 4)) >> 16) + ((yb1[:, None] * (rows[y1, :] >> 4)) >> 16) + 2) >> 2
+	return out.astype(np.uint8)
+
+
+def resize_nearest_u8(src, fx, fy):
+	H, W = src.shape
+	dw, dh = cv_round(W * fx), cv_round(H * fy)
+	xs = np.minimum(np.floor(np.arange(dw) * (1.0 / fx)).astype(np.int64), W - 1)
+	ys = np.minimum(np.floor(np.arange(dh) * (1.0 / fy)).astype(np.int64), H - 1)
+	return src[ys][:, xs]

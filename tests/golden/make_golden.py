@@ -131,6 +131,8 @@ CLIPS = {
 	'savgol_argmax': (dict(seed=2009, fc=150, shot_starts=[80]),
 					dict(loess_filt=0, com_km=False, lp_cutoff=1, lp_order=2), ['1:3']),
 	'border': (dict(seed=2010, fc=120), dict(t_border=10), ['1:3', '3:1']),
+	'best_settings': (dict(seed=2012, fc=240, shot_starts=[100]), 'BEST', ['1:3', '3:1']),
+	'best_hd_fr25': (dict(seed=2013, fc=150, w_orig=1920, h_orig=1080, fr=25.0), 'BEST', ['9:16']),
 }
 
 
@@ -145,7 +147,8 @@ def _with_empties(vd, rng):
 def make_clip_fixtures():
 	ref = ref_harness.load_reference()
 	specs = dict(CLIPS)
-	specs['empties'] = (dict(seed=2011, fc=240, shot_starts=[100]), {}, ['1:3'])
+	if specs.pop('__skip_empties__', 0) != None:
+		specs['empties'] = (dict(seed=2011, fc=240, shot_starts=[100]), {}, ['1:3'])
 	for name, (kw, over, ratios) in specs.items():
 		vd = synth.make_clip(**kw)
 		if name == 'border':
@@ -165,8 +168,9 @@ def make_clip_fixtures():
 		out['in_scalars'] = np.array([vd['fr'], vd['fc'], vd['fc_sel'], vd['h_orig'], vd['w_orig'],
 									vd['h_process'], vd['w_process']], dtype=np.float64)
 		for r in ratios:
-			CP = ref.sc_init_crop_params()
-			CP.update(over)
+			CP = ref.sc_init_crop_params(use_best_settings=(over == 'BEST'))
+			if over != 'BEST':
+				CP.update(over)
 			CP['out_ratio'] = r
 			VD, res, pre = _capture(vd, CP)
 			tag = r.replace(':', '-')
@@ -176,6 +180,8 @@ def make_clip_fixtures():
 										VD['border_l'], VD['border_r']], dtype=np.int32)
 			if r == ratios[0]:
 				out['smaps_filtered'] = np.asarray(VD['smaps'])
+				out['dxnf'] = _f(VD['dxnf'])
+				out['jumps'] = _f(VD['jumps'])
 				out['dx'] = _f(VD['dx'])
 				out['dy'] = _f(VD['dy'])
 				out['dxi'] = _f(VD['dxi'])
@@ -246,6 +252,12 @@ def make_hdbscan_fixture():
 
 if __name__ == '__main__':
 	only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None
+	if '--clip' in sys.argv:
+		keep = sys.argv[sys.argv.index('--clip') + 1].split(',')
+		for k in list(CLIPS.keys()):
+			if k not in keep:
+				del CLIPS[k]
+		CLIPS['__skip_empties__'] = None
 	if only in (None, 'eval'):
 		make_eval_fixture()
 	if only in (None, 'loess'):

@@ -7,7 +7,7 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 CLIP_NAMES = ['c1_default', 'multishot', 'fr25', 'hd1080', 'constant', 'noise', 'few_points',
-			'sumsel_min5', 'noclose_nolp', 'savgol_argmax', 'border', 'empties']
+			'sumsel_min5', 'noclose_nolp', 'savgol_argmax', 'border', 'empties', 'best_settings', 'best_hd_fr25']
 
 
 def load_clip_fixture(name):
@@ -21,6 +21,11 @@ def load_clip_fixture(name):
 			fr=float(sc[0]), fc=int(sc[1]), fc_sel=int(sc[2]), h_orig=int(sc[3]), w_orig=int(sc[4]),
 			h_process=int(sc[5]), w_process=int(sc[6]))
 	over = ast.literal_eval(str(fx['over']))
+	if over == 'BEST':
+		from oracle import sc_oracle
+		base = sc_oracle.sc_init_crop_params()
+		best = sc_oracle.sc_init_crop_params(use_best_settings=True)
+		over = {k: v for k, v in best.items() if base[k] != v}
 	ratios = [str(r) for r in fx['ratios']]
 	return vd, over, ratios, fx
 

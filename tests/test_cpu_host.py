@@ -177,3 +177,21 @@ def test_oracle_pyloess_and_eval_golden():
 		m = e['method_1-3'][moffs[i]:moffs[i + 1]].astype(int).tolist()
 		vals.append(eval_oracle.video_iou(m, a, len(a)))
 	assert all(0.0 <= v <= 1.0 for v in vals) and abs(statistics.mean(vals) - 0.5) < 0.25
+
+
+def test_cv_resize_restatement_matches_opencv():
+	"""oracle/cv_resize.py against cv2 itself (the library the reference calls, smartVidCrop.py:1080,1158,1184)."""
+	cv2 = pytest.importorskip('cv2')
+	from oracle import cv_resize
+	rng = np.random.default_rng(0)
+	for t in range(40):
+		H, W = (140, 250) if t % 2 == 0 else (int(rng.integers(20, 200)), int(rng.integers(20, 256)))
+		m = rng.integers(0, 256, (H, W)).astype(np.uint8)
+		if t % 3 == 0:
+			m[m < 150] = 0
+		for f in (4.0, 3.0, 1.5):
+			a = cv2.resize(m, None, fx=1.0 / f, fy=1.0 / f, interpolation=cv2.INTER_LINEAR)
+			assert np.array_equal(a, cv_resize.resize_linear_u8(m, fx=1.0 / f, fy=1.0 / f))
+			assert np.array_equal(cv2.resize(a, (W, H), interpolation=cv2.INTER_LINEAR), cv_resize.resize_linear_u8(a, dsize_wh=(W, H)))
+			assert np.array_equal(cv2.resize(m, None, fx=1.0 / f, fy=1.0 / f, interpolation=cv2.INTER_NEAREST),
+								cv_resize.resize_nearest_u8(m, 1.0 / f, 1.0 / f))
