@@ -62,10 +62,16 @@ typedef struct rvb_params {
 	int32_t shift_time;           /* smartVidCrop.py:1740-1746 */
 	int32_t exit_on_low_cvrg;     /* compute the coverage score, smartVidCrop.py:2380-2383 */
 	int32_t cvrg_window;          /* 0: reference (score == 0.0), 1: crop-sized window */
-	int32_t reserved0;
+	int32_t resize_type;          /* 1 bilinear, 3 nearest (2 = cubic is not built), smartVidCrop.py:1079-1084 */
+	int32_t focus_stability;      /* smartVidCrop.py:2427-2473 */
+	int32_t min_d_jump;
+	int32_t skip;                 /* frames between saliency maps, used by the focus-stability duration */
+	int32_t np_int_compat;        /* 0: numpy >= 1.24 (np.int raises, diagonal jumps give 255), 1: numpy the reference pins */
+	double  foces_stab_t;
+	double  foces_stab_s;
 	double  loess_w_secs;
 	double  lp_cutoff;
-	double  resize_factor;        /* must be 1.0 in this version */
+	double  resize_factor;        /* 1.0, or any factor except 2.0 (OpenCV's INTER_AREA special case) */
 	double  t_cvrg;
 } rvb_params;
 
@@ -101,7 +107,8 @@ typedef struct rvb_batch {
 	const void    *maps;          /* mem_space; for U8_HWN clip c starts at byte H*W*map_offset[c] */
 	/* ---- outputs, mem_space, caller allocated; optional ones may be NULL ---- */
 	int32_t *boxes;               /* [n_ratios][sum F][4] = x1,y1,x2,y2 (smartVidCrop.py:1046) */
-	double  *centres;             /* optional [2][sum N]: dx, dy after sc_handle_empty_centers (NaN never) */
+	double  *centres;             /* optional [2][sum N]: dx, dy after sc_handle_empty_centers and focus stability */
+	double  *centres_nf;          /* optional [3][sum N]: dxnf, dynf (before focus stability), jumps */
 	uint8_t *empty;               /* optional [sum N]: 1 where the filtered map was empty (dx is None) */
 	double  *series;              /* optional [6][sum F]: dxi, dyi, dxl, dyl, dxs, dys (dxs/dys before truncation) */
 	double  *map_scores;          /* optional [sum N]: mean_sal_scores (smartVidCrop.py:1307) */

@@ -45,7 +45,9 @@ class rvb_params(C.Structure):
 				('com_km', C.c_int32), ('t_border', C.c_int32), ('loess_filt', C.c_int32),
 				('loess_degree', C.c_int32), ('lp_filt', C.c_int32), ('lp_order', C.c_int32),
 				('shift_time', C.c_int32), ('exit_on_low_cvrg', C.c_int32), ('cvrg_window', C.c_int32),
-				('reserved0', C.c_int32), ('loess_w_secs', C.c_double), ('lp_cutoff', C.c_double),
+				('resize_type', C.c_int32), ('focus_stability', C.c_int32), ('min_d_jump', C.c_int32), ('skip', C.c_int32),
+				('np_int_compat', C.c_int32), ('foces_stab_t', C.c_double), ('foces_stab_s', C.c_double),
+				('loess_w_secs', C.c_double), ('lp_cutoff', C.c_double),
 				('resize_factor', C.c_double), ('t_cvrg', C.c_double)]
 
 
@@ -61,7 +63,8 @@ class rvb_batch(C.Structure):
 				('n_ratios', C.c_int32), ('reserved0', C.c_int32),
 				('ratio_w', C.c_double * RVB_MAX_RATIOS), ('ratio_h', C.c_double * RVB_MAX_RATIOS),
 				('clips', C.POINTER(rvb_clip)), ('shots', C.c_void_p), ('true_inds', C.c_void_p),
-				('maps', C.c_void_p), ('boxes', C.c_void_p), ('centres', C.c_void_p), ('empty', C.c_void_p),
+				('maps', C.c_void_p), ('boxes', C.c_void_p), ('centres', C.c_void_p), ('centres_nf', C.c_void_p),
+				('empty', C.c_void_p),
 				('series', C.c_void_p), ('map_scores', C.c_void_p), ('clip_scores', C.c_void_p),
 				('clip_dims', C.c_void_p), ('filtered_maps', C.c_void_p), ('row_stride_out', C.c_int32),
 				('reserved1', C.c_int32), ('map_info', C.c_void_p), ('clip_status', C.c_void_p),
@@ -113,7 +116,7 @@ def check(code):
 		raise RvbError(code, load_library().rvb_last_error().decode('utf-8', 'replace'))
 
 
-def params_from_crop_params(CP, cvrg_window='reference'):
+def params_from_crop_params(CP, cvrg_window='reference', np_int=False):
 	"""crop_params dict (sc_init_crop_params keys) -> rvb_params."""
 	p = rvb_params()
 	p.t_threshold = int(CP['t_threshold'])
@@ -131,6 +134,13 @@ def params_from_crop_params(CP, cvrg_window='reference'):
 	p.shift_time = int(CP['shift_time'])
 	p.exit_on_low_cvrg = 1 if CP['exit_on_low_cvrg'] else 0
 	p.cvrg_window = 1 if cvrg_window == 'crop' else 0
+	p.resize_type = int(CP['resize_type'])
+	p.focus_stability = 1 if CP['focus_stability'] else 0
+	p.min_d_jump = int(CP['min_d_jump'])
+	p.skip = int(CP['skip'])
+	p.np_int_compat = 1 if np_int else 0
+	p.foces_stab_t = float(CP['foces_stab_t'])
+	p.foces_stab_s = float(CP['foces_stab_s'])
 	p.loess_w_secs = float(CP['loess_w_secs'])
 	p.lp_cutoff = float(CP['lp_cutoff'])
 	p.resize_factor = float(CP['resize_factor'])

@@ -58,6 +58,7 @@ constexpr int kFlagClusterCapacity = 8;
 struct SmemLayout {
 	int pts;       // u16[NMAX]   (y << 8) | x, row-major order
 	int val;       // u8[NMAX]
+	int small;     // u8[Hs * WSs] down-scaled map (resize_factor != 1), else unused
 	int u_base;    // start of the overlaid region
 	// phase 0/1/5 view of the overlaid region
 	int map;       // u8[H * WPS]
@@ -109,6 +110,12 @@ struct MapArgs {
 	int n_ratios;
 	int32_t *labels_dbg;       // optional: labels of the single map being debugged
 	unsigned long long *phase_cycles;  // optional [16]: SM cycles spent per phase, summed over CTAs (profiling aid)
+	// resize_factor != 1 (smartVidCrop.py:1078-1084,1158,1184): cluster a down-scaled copy, scale the result back
+	int resize_on, resize_type;    // type 1: INTER_LINEAR, 3: INTER_NEAREST (down-scaling only)
+	int Hs, Ws, WSs;               // small size and its shared-memory row stride
+	double factor;
+	const int16_t *rz;             // coefficient tables, offsets below (int16 entries)
+	int rz_dx, rz_dy, rz_ux, rz_uy, rz_nx, rz_ny;   // down x/y: idx,a0,a1 ; up x/y: idx,a0,a1 ; nearest x/y: idx
 	// params
 	int t_threshold, clust_filt, mcs, min_samples, select_sum, op_close, com_km;
 	SmemLayout lay;
@@ -651,6 +658,26 @@ __device__ __forceinline__ void prim_dispatch(int ncnt, const uint16_t *pts, con
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv2.resize(..., INTER_LINEAR) for uint8 (OpenCV resize.cpp): horizontal pass in int with weights
+// scaled by 2048, vertical pass ((b * (S >> 4)) >> 16), + 2, >> 2, rows clipped.  Tables come from the
+// host (float32 source coordinates, weights rounded half-to-even).  src/dst live in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cv_resize_linear_u8(const uint8_t *src, int sH, int sW, int sstride, uint8_t *dst, int dH,
+													 int dW, int dstride, const int16_t *tx, const int16_t *ty, int NT) {
+	// tx: idx[dW], a0[dW], a1[dW]; ty: idx[dH], b0[dH], b1[dH]
+	for (int i = threadIdx.x; i < dH * dW; i += NT) {
+		const int y = i / dW, x = i - y * dW;
+		const int xi = tx[x], a0 = tx[dW + x], a1 = tx[2 * dW + x];
+		const int yi = ty[y], b0 = ty[dH + y], b1 = ty[2 * dH + y];
+		const int x1 = min(xi + 1, sW - 1);
+		const int y0 = min(max(yi, 0), sH - 1), y1 = min(max(yi + 1, 0), sH - 1);
+		const int r0 = ((int)src[y0 * sstride + xi] * a0 + (int)src[y0 * sstride + x1] * a1) >> 4;
+		const int r1 = ((int)src[y1 * sstride + xi] * a0 + (int)src[y1 * sstride + x1] * a1) >> 4;
+		dst[y * dstride + x] = (uint8_t)((((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2) >> 2);
+	}
+}
+
 // resident CTAs per SM the register budget must allow, per capacity class (shared memory bounds the same)
 template <int NT, int TPT>
 struct MapKernelCfg { static constexpr int kMinBlocks = (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1; };
@@ -757,7 +784,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			const uint8_t *pf = (pred >= 0) ? (a.filt + (size_t)pred * H * a.fstride) : nullptr;
 			const uint32_t thr4 = (uint32_t)a.t_threshold * 0x01010101u;
 			const int first_pad_word = W >> 2;
-			uint32_t raw = 0;
+			uint32_t raw = 0, post = 0;
 			for (int i = tid; i < n_words; i += NT) {
 				const int y = i / MWS, xw = i - y * MWS;
 				uint32_t v = map32[i];
@@ -779,28 +806,58 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 					v = (__vadd4(v, f) >> 1) & 0x7F7F7F7Fu;
 				}
 				map32[i] = v;
+				post += __vsadu4(v, 0u);
 			}
 			// border max profiles of the RAW map are taken before the threshold; they need a second
 			// look at the raw values, so they are handled by border_profile_kernel on request.
 			res.raw_sum = block_sum_u32<NT>(raw, S.red);
+			post = block_sum_u32<NT>(post, S.red);
+			if (tid == 0) S.tot = post;
 		}
 		__syncthreads();
+
+		// ---- resize_factor != 1: the clustering runs on a down-scaled copy (smartVidCrop.py:1078-1084);
+		// an all-zero map is returned untouched (:1064)
+		uint8_t *img8 = map8;
+		uint32_t *img32 = map32;
+		int LH = H, LW = W, LWPS = WPS;
+		const bool rz = a.resize_on && (S.tot != 0u);
+		if (rz) {
+			uint8_t *small8 = smem + L.small;
+			for (int i = tid; i < (a.Hs * a.WSs) >> 2; i += NT) reinterpret_cast<uint32_t *>(small8)[i] = 0u;
+			__syncthreads();
+			if (a.resize_type == 1) {
+				cv_resize_linear_u8(map8, H, W, WPS, small8, a.Hs, a.Ws, a.WSs, a.rz + a.rz_dx, a.rz + a.rz_dy, NT);
+			} else {
+				const int16_t *nx = a.rz + a.rz_nx, *ny = a.rz + a.rz_ny;
+				for (int i = tid; i < a.Hs * a.Ws; i += NT) {
+					const int y = i / a.Ws, x = i - y * a.Ws;
+					small8[y * a.WSs + x] = map8[ny[y] * WPS + nx[x]];
+				}
+			}
+			__syncthreads();
+			img8 = small8;
+			img32 = reinterpret_cast<uint32_t *>(small8);
+			LH = a.Hs; LW = a.Ws; LWPS = a.WSs;
+		}
+		const int LMWS = LWPS >> 2;
+		const int ln_words = LH * LMWS;
 
 		// ---- phase 1: compact the non-zero pixels in row-major order ----------------------------
 		int n;
 		{
-			const int chunk = (n_words + NT - 1) / NT;
-			const int w0 = tid * chunk, w1 = min(n_words, w0 + chunk);
+			const int chunk = (ln_words + NT - 1) / NT;
+			const int w0 = tid * chunk, w1 = min(ln_words, w0 + chunk);
 			uint32_t c = 0;
-			for (int i = w0; i < w1; ++i) c += __popc(__vcmpne4(map32[i], 0u)) >> 3;
+			for (int i = w0; i < w1; ++i) c += __popc(__vcmpne4(img32[i], 0u)) >> 3;
 			uint32_t total;
 			uint32_t base = block_excl_scan<NT>(c, S.red, total);
 			n = (int)total;
 			if (a.clust_filt && n <= L.nmax) {
 				for (int i = w0; i < w1; ++i) {
-					uint32_t v = map32[i];
+					uint32_t v = img32[i];
 					if (v == 0u) continue;
-					const int y = i / MWS, x0 = (i - y * MWS) * 4;
+					const int y = i / LMWS, x0 = (i - y * LMWS) * 4;
 #pragma unroll
 					for (int b = 0; b < 4; ++b) {
 						const uint32_t bv = (v >> (8 * b)) & 0xFFu;
@@ -858,14 +915,14 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			uint16_t *cl_ch1 = reinterpret_cast<uint16_t *>(smem + L.cl_ch1);
 			uint16_t *cl_label = reinterpret_cast<uint16_t *>(smem + L.cl_label);
 			uint16_t *cl_selanc = reinterpret_cast<uint16_t *>(smem + L.cl_selanc);
-			const int MW = (W + 31) >> 5;
+			const int MW = (LW + 31) >> 5;
 
 			// ---- phase 2: core distances on the lattice -------------------------------------------
 			// k-th nearest OTHER salient pixel (hdbscan: sorted-row index min_samples, self at 0).
 			int kk = (a.min_samples > 0) ? a.min_samples : a.mcs;
 			kk = min(n - 1, kk);
 			if (kk == 0) kk = 1;
-			for (int i = tid; i < H * MW; i += NT) mask[i] = 0u;
+			for (int i = tid; i < LH * MW; i += NT) mask[i] = 0u;
 			if (tid == 0) S.fb_count = 0;
 			__syncthreads();
 			for (int p = tid; p < n; p += NT) {
@@ -884,7 +941,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 					if (active) {
 						for (; i < e; ++i) {
 							const int yy = y + c_rings.dy[i], xx = x + c_rings.dx[i];
-							if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W)
+							if ((unsigned)yy < (unsigned)LH && (unsigned)xx < (unsigned)LW)
 								cnt += (mask[yy * MW + (xx >> 5)] >> (xx & 31)) & 1u;
 						}
 						if (cnt >= kk) {
@@ -910,7 +967,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 				for (int f = warp; f < fbn; f += NW) {
 					const int p = queue[f];
 					const int y = pts[p] >> 8, x = pts[p] & 0xFF;
-					int lo = kRingD2Max + 1, hi = H * H + W * W;
+					int lo = kRingD2Max + 1, hi = LH * LH + LW * LW;
 					while (lo < hi) {
 						const int mid = (lo + hi) >> 1;
 						int c = 0;
@@ -1126,21 +1183,30 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 
 			RVB_PHASE(8);  // EOM + labels + dominant cluster
 			// ---- phase 5: rebuild the map, close it --------------------------------------------------
-			for (int i = tid; i < n_words; i += NT) map32[i] = 0u;
+			for (int i = tid; i < ln_words; i += NT) img32[i] = 0u;
 			__syncthreads();
-			for (int p = tid; p < n; p += NT) map8[(pts[p] >> 8) * WPS + (pts[p] & 0xFF)] = val[p];
+			for (int p = tid; p < n; p += NT) img8[(pts[p] >> 8) * LWPS + (pts[p] & 0xFF)] = val[p];
 			__syncthreads();
 			rebuilt = true;
 			if (a.op_close && S.n_clusters > 0) {
-				morph_pass_h<NT, true>(map32, H, MWS);
-				morph_pass_v<NT, true>(map32, H, MWS);
-				set_row_padding(map32, H, W, MWS, 0xFFu, NT);
+				morph_pass_h<NT, true>(img32, LH, LMWS);
+				morph_pass_v<NT, true>(img32, LH, LMWS);
+				set_row_padding(img32, LH, LW, LMWS, 0xFFu, NT);
 				__syncthreads();
-				morph_pass_h<NT, false>(map32, H, MWS);
-				morph_pass_v<NT, false>(map32, H, MWS);
-				set_row_padding(map32, H, W, MWS, 0x00u, NT);
+				morph_pass_h<NT, false>(img32, LH, LMWS);
+				morph_pass_v<NT, false>(img32, LH, LMWS);
+				set_row_padding(img32, LH, LW, LMWS, 0x00u, NT);
 				__syncthreads();
 			}
+		}
+		if (rz) {
+			// cv2.resize(small, (initW, initH), INTER_LINEAR) -- smartVidCrop.py:1158, also when the gates skipped
+			// the clustering.  The full-size buffer was re-used by the clustering state: rebuild it completely.
+			__syncthreads();
+			for (int i = tid; i < n_words; i += NT) map32[i] = 0u;
+			__syncthreads();
+			cv_resize_linear_u8(img8, LH, LW, LWPS, map8, H, W, WPS, a.rz + a.rz_ux, a.rz + a.rz_uy, NT);
+			__syncthreads();
 		}
 		(void)rebuilt;
 
@@ -1180,7 +1246,29 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 		}
 		__syncthreads();
 		res.kept_points = (int)S.cnt;
-		if (S.tot == 0u) {
+		if (S.tot != 0u && a.com_km && a.resize_on) {
+			// sc_find_center_of_mass down-samples with INTER_NEAREST by the same factor (smartVidCrop.py:1184)
+			// and scales the centroid of the non-zero samples back (:1212-1213)
+			const int16_t *nx = a.rz + a.rz_nx, *ny = a.rz + a.rz_ny;
+			__syncthreads();
+			if (tid == 0) { S.sx = 0ull; S.sy = 0ull; S.cnt = 0u; }
+			__syncthreads();
+			uint32_t cnt = 0, sx = 0, sy = 0;
+			for (int i = tid; i < a.Hs * a.Ws; i += NT) {
+				const int y = i / a.Ws, x = i - y * a.Ws;
+				if (map8[ny[y] * WPS + nx[x]]) { ++cnt; sx += x; sy += y; }
+			}
+			cnt = __reduce_add_sync(0xffffffffu, cnt);
+			sx = __reduce_add_sync(0xffffffffu, sx);
+			sy = __reduce_add_sync(0xffffffffu, sy);
+			if (lane == 0) { atomicAdd(&S.cnt, cnt); atomicAdd(&S.sx, (unsigned long long)sx); atomicAdd(&S.sy, (unsigned long long)sy); }
+			__syncthreads();
+			if (S.cnt == 0u) res.flags |= kFlagEmpty;
+			else {
+				res.cx = ((double)S.sx / (double)S.cnt) * a.factor;
+				res.cy = ((double)S.sy / (double)S.cnt) * a.factor;
+			}
+		} else if (S.tot == 0u) {
 			res.flags |= kFlagEmpty;
 		} else if (a.com_km) {
 			// KMeans(n_clusters=1) == unweighted centroid of the non-zero pixels

@@ -103,7 +103,7 @@ struct rvb_ctx {
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
 static const int kMaxDynSmem = 227 * 1024 - 1024;  // per-CTA opt-in limit minus the kernel's static shared memory
 
-static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs) {
+static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs, int small_bytes) {
 	SmemLayout L;
 	memset(&L, 0, sizeof(L));
 	int o = 0;
@@ -112,6 +112,7 @@ static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs) {
 	L.ncmax = std::min(2 * nmax / std::max(mcs, 2) + 3, nmax > 4096 ? 770 : nmax / 2 + 2);
 	L.pts = o; o += align_up(std::max(2 * nmax, 4 * std::max(H, W)), 16);
 	L.val = o; o += align_up(nmax, 16);
+	L.small = o; o += align_up(small_bytes, 16);
 	o = align_up(o, 128);
 	L.u_base = o;
 	L.map = o;
@@ -234,6 +235,55 @@ static void butter_design(int order, double wn, FilterCoef &fc) {
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv2.resize coefficient tables (OpenCV resize.cpp): float32 source coordinate, weights * 2048 rounded
+// half-to-even; the horizontal table clamps at the borders, the vertical one keeps its weights (rows are
+// clipped by the kernel).  Layout per axis: idx[d], w0[d], w1[d].
+// ---------------------------------------------------------------------------------------------
+static int cv_round_d(double v) { return (int)nearbyint(v); }
+
+static void linear_table(int dsize, int ssize, double scale, bool vertical, std::vector<int16_t> &out) {
+	const size_t base = out.size();
+	out.resize(base + 3 * (size_t)dsize);
+	for (int d = 0; d < dsize; ++d) {
+		float f = (float)((d + 0.5) * scale - 0.5);
+		int sidx = (int)floorf(f);
+		f -= (float)sidx;
+		if (!vertical) {
+			if (sidx < 0) { sidx = 0; f = 0.f; }
+			if (sidx >= ssize - 1) { sidx = ssize - 1; f = 0.f; }
+		}
+		out[base + d] = (int16_t)sidx;
+		out[base + dsize + d] = (int16_t)nearbyintf((1.f - f) * 2048.f);
+		out[base + 2 * (size_t)dsize + d] = (int16_t)nearbyintf(f * 2048.f);
+	}
+}
+
+static void nearest_table(int dsize, int ssize, double fx, std::vector<int16_t> &out) {
+	const double ifx = 1.0 / fx;
+	for (int d = 0; d < dsize; ++d) out.push_back((int16_t)std::min((int)floor(d * ifx), ssize - 1));
+}
+
+struct ResizeSetup {
+	int on = 0, Hs = 0, Ws = 0, WSs = 0;
+	int dx = 0, dy = 0, ux = 0, uy = 0, nx = 0, ny = 0;
+	std::vector<int16_t> tab;
+};
+
+static void build_resize(double factor, int H, int W, ResizeSetup &r) {
+	r.on = 1;
+	const double fx = 1.0 / factor;
+	r.Ws = cv_round_d(W * fx);
+	r.Hs = cv_round_d(H * fx);
+	r.WSs = align_up(r.Ws, 16);
+	r.dx = (int)r.tab.size(); linear_table(r.Ws, W, 1.0 / fx, false, r.tab);
+	r.dy = (int)r.tab.size(); linear_table(r.Hs, H, 1.0 / fx, true, r.tab);
+	r.ux = (int)r.tab.size(); linear_table(W, r.Ws, 1.0 / ((double)W / r.Ws), false, r.tab);
+	r.uy = (int)r.tab.size(); linear_table(H, r.Hs, 1.0 / ((double)H / r.Hs), true, r.tab);
+	r.nx = (int)r.tab.size(); nearest_table(r.Ws, W, fx, r.tab);
+	r.ny = (int)r.tab.size(); nearest_table(r.Hs, H, fx, r.tab);
+}
+
 // sc_calc_dest_size -- smartVidCrop.py:946-977
 static void calc_dest_size(int w_orig, int h_orig, double tw, double th, int out[3]) {
 	const double orig_ratio = (double)w_orig / (double)h_orig;
@@ -351,11 +401,12 @@ extern "C" int rvb_params_default(rvb_params *p, int use_best_settings) {
 	p->t_threshold = 120; p->clust_filt = 1; p->hdbscan_min = 26; p->hdbscan_min_samples = 0;
 	p->select_sum = 2; p->op_close = 1; p->com_km = 1; p->t_border = -1;
 	p->loess_filt = 1; p->loess_degree = 2; p->lp_filt = 1; p->lp_order = 5; p->shift_time = 0;
-	p->exit_on_low_cvrg = 0; p->cvrg_window = 0;
+	p->exit_on_low_cvrg = 0; p->cvrg_window = 0; p->resize_type = 1; p->focus_stability = 0; p->min_d_jump = 10;
+	p->skip = 6; p->np_int_compat = 0; p->foces_stab_t = 60.0; p->foces_stab_s = 1.5;
 	p->loess_w_secs = 2.0; p->lp_cutoff = 2.0; p->resize_factor = 1.0; p->t_cvrg = 0.60;
 	if (use_best_settings) {
 		p->t_threshold = 90; p->hdbscan_min = 5; p->hdbscan_min_samples = 3; p->resize_factor = 4.0;
-		p->select_sum = 1; p->lp_cutoff = 1.0; p->lp_order = 2; p->loess_filt = 0;
+		p->select_sum = 1; p->lp_cutoff = 1.0; p->lp_order = 2; p->loess_filt = 0; p->focus_stability = 1; p->min_d_jump = 1;
 	}
 	return RVB_OK;
 }
@@ -363,7 +414,7 @@ extern "C" int rvb_params_default(rvb_params *p, int use_best_settings) {
 // one launch of the map kernel family
 template <int NT, int TPT>
 static int launch_map(rvb_ctx *c, MapArgs a, int H, int W, int WPS, int grid) {
-	a.lay = make_layout(NT * TPT, H, WPS, W, a.mcs);
+	a.lay = make_layout(NT * TPT, H, WPS, W, a.mcs, a.resize_on ? a.Hs * a.WSs : 0);
 	if (a.lay.total > (NT * TPT > 4096 ? kMaxDynSmem : 200 * 1024)) return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d needs %d B of shared memory", H, W, a.lay.total);
 	map_kernel<NT, TPT><<<grid, NT, a.lay.total, c->stream>>>(a);
 	CU(cudaGetLastError());
@@ -395,8 +446,12 @@ struct Staging {  // packs the small per-call arrays into one pinned block -> on
 
 extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_batch *b) {
 	if (!c || !p || !b) return fail(RVB_ERR_INVALID, "NULL argument");
-	if (p->resize_factor != 1.0)
-		return fail(RVB_ERR_UNSUPPORTED, "resize_factor=%g: only 1.0 is built (SURVEY.md 8f)", p->resize_factor);
+	if (p->resize_factor != 1.0) {
+		if (!(p->resize_factor > 1.0) || p->resize_factor == 2.0)
+			return fail(RVB_ERR_UNSUPPORTED, "resize_factor=%g (must be 1 or > 1 and not 2: OpenCV resizes by exactly 2 with INTER_AREA)", p->resize_factor);
+		if (p->resize_type != 1 && p->resize_type != 3)
+			return fail(RVB_ERR_UNSUPPORTED, "resize_type=%d: only bilinear (1) and nearest (3) are built", p->resize_type);
+	}
 	if (b->n_clips <= 0) return fail(RVB_ERR_INVALID, "n_clips=%d", b->n_clips);
 	if (b->n_ratios < 1 || b->n_ratios > RVB_MAX_RATIOS) return fail(RVB_ERR_INVALID, "n_ratios=%d", b->n_ratios);
 	const int H = b->h_process, W = b->w_process;
@@ -435,6 +490,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	long long scratch_doubles = 0;
 	int n_slots = 0;
 	const bool want_filtered = b->filtered_maps != nullptr;
+	const bool keep_all_maps = want_filtered || p->focus_stability;  // focus stability samples every filtered map
 	for (int i = 0; i < nc; ++i) {
 		const rvb_clip &cl = b->clips[i];
 		ClipDev &d = clips[i];
@@ -476,7 +532,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				}
 			}
 		}
-		if (want_filtered)
+		if (keep_all_maps)
 			for (int k = 0; k < cl.n_maps; ++k) if (store[d.map_offset + k] < 0) store[d.map_offset + k] = n_slots++;
 		for (int r = 0; r < R; ++r) {
 			int fin[3];
@@ -527,6 +583,11 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_ccoef = sg.add(clip_coef.data(), clip_coef.size() * sizeof(int));
 	const size_t o_coefs = sg.add(coefs.data(), coefs.size() * sizeof(FilterCoef));
 	const size_t o_cnt = sg.add(counters.data(), counters.size() * sizeof(int));
+	ResizeSetup rzs;
+	if (p->resize_factor != 1.0) build_resize(p->resize_factor, H, W, rzs);
+	const size_t o_rz = sg.add(rzs.tab.data(), rzs.tab.size() * sizeof(int16_t));
+	const int small_bytes = rzs.on ? rzs.Hs * rzs.WSs : 0;
+	const size_t o_jumps = sg.add(nullptr, (size_t)NM * sizeof(double));
 	const size_t o_work = sg.add(work.data(), work.size() * sizeof(int));
 	const size_t o_ovf1 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
@@ -632,6 +693,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.border_prof = nullptr;
 	a.cvrg_cfg = p->exit_on_low_cvrg ? (const int *)(M + o_cvrg) : nullptr;
 	a.n_ratios = R; a.labels_dbg = nullptr;
+	a.resize_on = rzs.on; a.resize_type = p->resize_type; a.Hs = rzs.Hs; a.Ws = rzs.Ws; a.WSs = rzs.WSs; a.factor = p->resize_factor;
+	a.rz = (const int16_t *)(M + o_rz); a.rz_dx = rzs.dx; a.rz_dy = rzs.dy; a.rz_ux = rzs.ux; a.rz_uy = rzs.uy; a.rz_nx = rzs.nx; a.rz_ny = rzs.ny;
 	a.phase_cycles = c->phase_on ? (unsigned long long *)c->phase.p : nullptr;
 	a.t_threshold = p->t_threshold; a.clust_filt = p->clust_filt; a.mcs = p->hdbscan_min;
 	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
@@ -655,11 +718,11 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 			a.ovf_list = (k < 4) ? ovf[k] : nullptr;
 			a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
 			int rc = RVB_OK;
-			if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs).total, nw));
-			if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs).total, nw));
-			if (k == 2) rc = launch_map<256, 12>(c, a, H, W, WPS, occupancy_grid<256, 12>(c, make_layout(3072, H, WPS, W, mcs).total, nw));
-			if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs).total, nw));
-			if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs).total, nw));
+			if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nw));
+			if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nw));
+			if (k == 2) rc = launch_map<256, 12>(c, a, H, W, WPS, occupancy_grid<256, 12>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nw));
+			if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nw));
+			if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nw));
 			if (rc) return rc;
 		}
 	}
@@ -681,6 +744,21 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	uint8_t *d_empty = M + o_empty;
 
 	fill_centres_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_shots, d_mo, d_dx, d_dy, d_empty, d_status);
+	double *d_jumps = (double *)(M + o_jumps);
+	if (b->centres_nf) {  // dxnf, dynf: the centres before focus stability (smartVidCrop.py:2450-2451)
+		const cudaMemcpyKind knf = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+		CU(cudaMemcpyAsync(b->centres_nf, d_dx, (size_t)2 * NM * sizeof(double), knf, st));
+	}
+	if (p->focus_stability) {
+		focus_jumps_kernel<<<(NM + 127) / 128, 128, 0, st>>>(d_clips, (const int *)(M + o_mclip), NM, d_dx, d_dy, (const uint8_t *)c->filt.p,
+															 (const int *)(M + o_store), H, W, WPS, (double)p->min_d_jump, p->np_int_compat, d_jumps);
+		focus_apply_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_jumps, p->foces_stab_t, p->foces_stab_s, p->skip, d_dx, d_dy);
+		c->launches += 2;
+	}
+	if (b->centres_nf) {
+		const cudaMemcpyKind knf = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+		if (p->focus_stability) CU(cudaMemcpyAsync(b->centres_nf + 2 * (size_t)NM, d_jumps, (size_t)NM * sizeof(double), knf, st));
+	}
 	spline_setup_kernel<<<(NS + 63) / 64, 64, 0, st>>>(d_shots, NS, d_ti, d_dx, d_dy, d_scratch);
 	interp_eval_kernel<<<(NF + 255) / 256, 256, 0, st>>>(d_shots, d_fshot, NF, d_ti, d_dx, d_dy, d_scratch, d_dxi, d_dyi);
 	lowpass_kernel<<<(2 * NS + 63) / 64, 64, 0, st>>>(d_shots, NS, d_clips, (const FilterCoef *)(M + o_coefs),

@@ -79,6 +79,86 @@ __global__ void fill_centres_kernel(const ClipDev *clips, int n_clips, const Sho
 }
 
 // ---------------------------------------------------------------------------------------------
+// focus stability: get_points_on_line smartVidCrop.py:1337-1393, sc_check_for_extra_cuts
+// :1395-1455, driver :2424-2473.  jumps[i] = mean saliency of filtered map i under the segment from centre
+// i-1 to centre i (255 when the move is shorter than min_d_jump).  `np.int` (:1377,1384) does not exist in
+// numpy >= 1.24: there every diagonal move raises inside the reference's try/except and yields 255
+// (np_int == 0, the behaviour of this image's numpy); np_int == 1 restates the pinned numpy.
+// One thread per map, then one thread per clip for the freeze pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void focus_jumps_kernel(const ClipDev *clips, const int *map_clip, int n_maps_total, const double *dx,
+								   const double *dy, const uint8_t *filt, const int *store, int H, int W, int fstride,
+								   double min_d, int np_int, double *jumps) {
+	const int m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= n_maps_total) return;
+	const ClipDev cl = clips[map_clip[m]];
+	double out = 255.0;
+	if (m > cl.map_offset) {
+		const double p1x = dx[m - 1], p1y = dy[m - 1], p2x = dx[m], p2y = dy[m];
+		const double dX = p2x - p1x, dY = p2y - p1y, dXa = fabs(dX), dYa = fabs(dY);
+		if (!(dXa < min_d && dYa < min_d)) {
+			const int np = (int)ceil(fmax(dYa, dXa));
+			const bool negY = p1y > p2y, negX = p1x > p2x;
+			const uint8_t *img = filt + (size_t)store[m] * H * fstride;
+			int mode = 0;  // 1 vertical, 2 horizontal, 3 steep diagonal, 4 shallow diagonal
+			if (p1x == p2x) mode = 1;
+			else if (p1y == p2y) mode = 2;
+			else if (np_int) mode = (dYa > dXa) ? 3 : 4;
+			// np.arange(a, a + d) has ceil(d) elements; a length mismatch with the buffer raises -> 255
+			const int nlen = (mode == 1 || mode == 3) ? (int)ceil(dYa) : (int)ceil(dXa);
+			if (mode != 0 && nlen == np) {
+				double sum = 0.0;
+				int cnt = 0;
+				float slope = 0.f;
+				if (mode == 3) slope = (float)dX / (float)dY;
+				if (mode == 4) slope = (float)dY / (float)dX;
+				for (int k = 1; k <= np; ++k) {
+					float fx, fy;
+					if (mode == 1 || mode == 3) {
+						fy = (float)(negY ? (p1y - (double)k) : (p1y + (double)k));
+						if (mode == 1) fx = (float)p1x;
+						else fx = (float)((double)(long long)(slope * (fy - (float)p1y)) + p1x);
+					} else {
+						fx = (float)(negX ? (p1x - (double)k) : (p1x + (double)k));
+						if (mode == 2) fy = (float)p1y;
+						else fy = (float)((double)(long long)(slope * (fx - (float)p1x)) + p1y);
+					}
+					if (fx >= 0.f && fy >= 0.f && fx < (float)W && fy < (float)H) {
+						++cnt;
+						sum += (double)img[(int)floorf(fy) * fstride + (int)floorf(fx)];
+					}
+				}
+				out = (cnt > 0) ? (sum / (double)cnt) : 255.0;
+			}
+		}
+	}
+	jumps[m] = out;
+}
+
+__global__ void focus_apply_kernel(const ClipDev *clips, int n_clips, const double *jumps, double thr, double max_secs,
+								   int skip, double *dx, double *dy) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_clips) return;
+	const ClipDev cl = clips[c];
+	const int N = cl.n_maps, base = cl.map_offset;
+	int prev = -1;  // previous index with jumps < thr
+	for (int i = 1; i < N; ++i) {
+		if (!(jumps[base + i] < thr)) continue;
+		if (prev >= 0) {
+			const int start = max(prev - 1, 0), end = min(i + 1, N - 1);
+			const double dur = ((double)((end - start) * skip)) / cl.fr;
+			if (!(dur > max_secs)) {
+				for (int j = 0; j < end - start; ++j) {
+					dx[base + start + j] = dx[base + start];
+					dy[base + start + j] = dy[base + start];
+				}
+			}
+		}
+		prev = i;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // a10: interp_handler / sc_interpolate, smartVidCrop.py:1528-1597.
 // scipy.interpolate.interp1d(kind='linear'|'quadratic', fill_value='extrapolate').  The quadratic
 // kind is make_interp_spline(k=2): knots x0 x0 x0, midpoints m_1..m_{n-3}, x_{n-1} x3, a banded

@@ -18,7 +18,7 @@ def parse_ratio(out_ratio):
 
 class ClipResult(object):
 	"""Per-clip outputs of one batched call (numpy views / python scalars)."""
-	__slots__ = ('status', 'boxes', 'dx', 'dy', 'empty', 'series', 'map_scores', 'mean_sal_score',
+	__slots__ = ('status', 'boxes', 'dx', 'dy', 'dxnf', 'dynf', 'jumps', 'empty', 'series', 'map_scores', 'mean_sal_score',
 				'cvrg_scores', 'dims', 'map_info', 'filtered')
 
 
@@ -105,9 +105,11 @@ class CropEngine(object):
 		b.clip_dims = dims.ctypes.data
 		cscores = np.zeros((nc, 1 + R), dtype=np.float64)
 		b.clip_scores = cscores.ctypes.data
-		centres = series = empty = mscores = minfo = filt = None
+		centres = series = empty = mscores = minfo = filt = cnf = None
 		if detail:
 			centres = np.empty((2, NM), dtype=np.float64)
+			cnf = np.full((3, NM), 255.0, dtype=np.float64)
+			b.centres_nf = cnf.ctypes.data
 			series = np.empty((6, NF), dtype=np.float64)
 			empty = np.empty(NM, dtype=np.uint8)
 			mscores = np.empty(NM, dtype=np.float64)
@@ -139,7 +141,11 @@ class CropEngine(object):
 			res.mean_sal_score = float(cscores[i, 0])
 			res.cvrg_scores = cscores[i, 1:]
 			res.dx = res.dy = res.empty = res.series = res.map_scores = res.map_info = res.filtered = None
+			res.dxnf = res.dynf = res.jumps = None
 			if detail:
+				res.dxnf = cnf[0, m0:m1]
+				res.dynf = cnf[1, m0:m1]
+				res.jumps = cnf[2, m0:m1]
 				res.dx = centres[0, m0:m1]
 				res.dy = centres[1, m0:m1]
 				res.empty = empty[m0:m1]

@@ -93,12 +93,11 @@ def smart_crop_version():
 
 
 def _check_supported(CP):
-	if CP['focus_stability']:
-		raise NotImplementedError('focus_stability is not built yet (SURVEY.md 8f-2); set CP["focus_stability"]=False')
 	if float(CP['resize_factor']) != 1.0:
-		raise NotImplementedError('resize_factor != 1 is not built yet (SURVEY.md 8f); set CP["resize_factor"]=1.0')
-	if CP['exit_on_spread_sal'] and False:
-		pass
+		if not float(CP['resize_factor']) > 1.0 or float(CP['resize_factor']) == 2.0:
+			raise NotImplementedError('resize_factor=%r: exact 2x (OpenCV switches to INTER_AREA) and up-scaling are not built' % CP['resize_factor'])
+		if CP['resize_type'] not in (1, 3):
+			raise NotImplementedError('resize_type=2 (cubic) is not built')
 
 
 def _times_dict(vid_dur, t_map, t_total, ingest_times):
@@ -142,10 +141,11 @@ def _fill_vd(VD, CP, res, ratio_index, want_smaps):
 	dy = [float(v) for v in res.dy]
 	VD['dx'] = dx
 	VD['dy'] = dy
-	VD['dxnf'] = list(dx)
-	VD['dynf'] = list(dy)
-	VD['jumps'] = [255] * len(dx)
-	VD['jumps_inds'] = []
+	VD['dxnf'] = [float(v) for v in res.dxnf]
+	VD['dynf'] = [float(v) for v in res.dynf]
+	jumps = [float(v) for v in res.jumps]
+	VD['jumps'] = [255 if v == 255.0 else v for v in jumps]
+	VD['jumps_inds'] = [i for i in range(1, len(jumps)) if CP['focus_stability'] and jumps[i] < CP['foces_stab_t']]
 	s = res.series
 	VD['dxi'] = [float(v) for v in s[0]]
 	VD['dyi'] = [float(v) for v in s[1]]

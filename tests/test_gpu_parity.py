@@ -233,9 +233,10 @@ def test_error_behaviour(engine):
 	with pytest.raises(_cabi.RvbError) as ei:
 		svc.smart_vid_crop('x.mp4', CP2, save_vid=False, vid_data=synth.make_clip(2, fc=30))
 	assert ei.value.code == _cabi.RVB_ERR_CAPACITY
+	CP3 = svc.sc_init_crop_params(use_best_settings=True)
+	CP3['resize_factor'] = 2   # OpenCV resizes by exactly 2 with INTER_AREA: not built, must be loud
 	with pytest.raises(NotImplementedError):
-		svc.smart_vid_crop('x.mp4', svc.sc_init_crop_params(use_best_settings=True), save_vid=False,
-						vid_data=synth.make_clip(3, fc=30))
+		svc.smart_vid_crop('x.mp4', CP3, save_vid=False, vid_data=synth.make_clip(3, fc=30))
 
 
 def _run_raw(engine, vds, CP, ratios, maps_kind, maps_arrays):
@@ -411,3 +412,30 @@ def test_coverage_score_crop_window_and_padding_fallback(engine):
 	CP3['t_cvrg'] = 1.01
 	VD, info = svc.smart_vid_crop('c4.mp4', CP3, save_vid=False, vid_data=dict(vd), cvrg_window='crop')
 	assert info['result'] == 'padded' and 'bbs' not in VD and info['coverage_score'] == want['mean_cvrg_score']
+
+
+def test_focus_stability_sampling_paths(engine):
+	"""focus stability with integer centres (com_km=False) so that vertical / horizontal moves occur, and with
+	the pinned-numpy behaviour (np_int) for diagonal moves: jumps, frozen centres and boxes equal the oracle."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vd = synth.make_clip(5150, fc=200, shot_starts=[90])
+	for np_int in (False, True):
+		CP = svc.sc_init_crop_params()
+		CP.update(dict(focus_stability=True, com_km=False, min_d_jump=1, foces_stab_t=200, foces_stab_s=3.0, out_ratio='1:3'))
+		want = sc_oracle.smart_vid_crop_oracle(vd, CP, np_int=np_int)
+		engine_params = _cabi.params_from_crop_params(CP, np_int=np_int)
+		# run through the engine with the chosen numpy-compat flag
+		orig = _cabi.params_from_crop_params
+		_cabi.params_from_crop_params = lambda cp, cw='reference', np_int=np_int: orig(cp, cw, np_int)
+		try:
+			res = engine.run([vd], CP, ['1:3'], detail=True)[0]
+		finally:
+			_cabi.params_from_crop_params = orig
+		assert np.allclose(res.jumps, np.array(want['jumps'], dtype=np.float64), rtol=0, atol=1e-9), np_int
+		assert np.array_equal(res.dx, np.array(want['dx'], dtype=np.float64))
+		assert np.array_equal(res.dxnf, np.array(want['dxnf'], dtype=np.float64))
+		assert np.array_equal(res.boxes[0], np.array(want['bbs'], dtype=np.int32))
+		assert any(j != 255 for j in want['jumps'])
