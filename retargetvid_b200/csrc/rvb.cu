@@ -331,7 +331,7 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	CU(cudaMemcpyToSymbol(c_rings, &t, sizeof(t)));
 	CU(cudaFuncSetAttribute(map_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-	CU(cudaFuncSetAttribute(map_kernel<256, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
 	*out = c;
@@ -720,7 +720,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 			int rc = RVB_OK;
 			if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nw));
 			if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nw));
-			if (k == 2) rc = launch_map<256, 12>(c, a, H, W, WPS, occupancy_grid<256, 12>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nw));
+			if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nw));
 			if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nw));
 			if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nw));
 			if (rc) return rc;
@@ -955,7 +955,7 @@ extern "C" int rvb_debug_cluster_labels(rvb_ctx *c, const rvb_params *p, const u
 	int rc;
 	if (n <= 1536) rc = launch_map<256, 6>(c, a, h, w, WPS, 1);
 	else if (n <= 2048) rc = launch_map<256, 8>(c, a, h, w, WPS, 1);
-	else if (n <= 3072) rc = launch_map<256, 12>(c, a, h, w, WPS, 1);
+	else if (n <= 3072) rc = launch_map<512, 6>(c, a, h, w, WPS, 1);
 	else if (n <= 4096) rc = launch_map<512, 8>(c, a, h, w, WPS, 1);
 	else rc = launch_map<512, 16>(c, a, h, w, WPS, 1);
 	if (rc) return rc;

@@ -439,3 +439,36 @@ def test_focus_stability_sampling_paths(engine):
 		assert np.array_equal(res.dxnf, np.array(want['dxnf'], dtype=np.float64))
 		assert np.array_equal(res.boxes[0], np.array(want['bbs'], dtype=np.int32))
 		assert any(j != 255 for j in want['jumps'])
+
+
+@pytest.mark.parametrize('w_orig,h_orig', [(480, 360), (360, 640), (1000, 250)])
+def test_other_process_sizes(engine, w_orig, h_orig):
+	"""4:3 (187x250 maps), portrait (250x140) and very wide (62x250) inputs against the oracle."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vd = synth.make_clip(9000 + w_orig, fc=80, w_orig=w_orig, h_orig=h_orig, shot_starts=[37])
+	CP = svc.sc_init_crop_params()
+	CP['out_ratio'] = '1:1'
+	res = engine.run([vd], CP, ['1:1', '9:16'], detail=True, want_filtered=True)[0]
+	want = sc_oracle.smart_vid_crop_oracle(vd, CP)
+	assert np.array_equal(np.transpose(res.filtered, (1, 2, 0)), want['smaps_filtered'])
+	assert np.array_equal(res.boxes[0], np.array(want['bbs'], dtype=np.int32))
+	assert np.max(np.abs(res.series[4] - np.array(want['dxs']))) <= 1e-8
+
+
+def test_ragged_batch_and_tiny_clips(engine):
+	"""clips of 1, 2, 3 frames, a clip whose every shot is shorter than the filtfilt pad, mixed process sizes in one call."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vds = [synth.make_clip(9100, fc=1), synth.make_clip(9101, fc=2), synth.make_clip(9102, fc=3),
+		synth.make_clip(9103, fc=40, shot_starts=[9, 17, 26, 31]), synth.make_clip(9104, fc=30, w_orig=480, h_orig=360),
+		synth.make_clip(9105, fc=25, kind='single_pixel')]
+	CP = svc.sc_init_crop_params()
+	CP['out_ratio'] = '3:1'
+	res = engine.run(vds, CP, ['3:1'], detail=True)
+	for vd, r in zip(vds, res):
+		want = sc_oracle.smart_vid_crop_oracle(vd, CP)
+		assert r.status == 0
+		assert np.array_equal(r.boxes[0], np.array(want['bbs'], dtype=np.int32))
