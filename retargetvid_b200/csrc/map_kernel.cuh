@@ -460,19 +460,21 @@ __device__ void np_aquicksort_block(uint32_t *t, int num, uint16_t *ilist, uint1
 // separable 5x5 max / min on a byte image held in shared memory (words of 4 pixels).
 // OpenCV's default morphology border never wins, i.e. windows are clipped to the image.
 // ---------------------------------------------------------------------------------------------
+// The passes only visit the rectangle rows [ry0, ry1] x words [xw0, xw1] (the kept pixels' bounding box grown by
+// the 2-pixel reach of the 5x5 window): everything outside is zero before and after a closing.
 template <int NT, bool IS_MAX>
-__device__ __forceinline__ void morph_pass_h(uint32_t *img, int H, int MWS) {
+__device__ __forceinline__ void morph_pass_h(uint32_t *img, int H, int MWS, int ry0, int ry1, int xw0, int xw1) {
 	// 1x5 along x, in place: one warp owns a row, loads everything it needs, then stores
 	const uint32_t neutral = IS_MAX ? 0u : 0xFFFFFFFFu;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (int y = warp; y < H; y += NT / 32) {
+	for (int y = ry0 + warp; y <= ry1; y += NT / 32) {
 		uint32_t *row = img + y * MWS;
 		uint32_t res[2];
 #pragma unroll
 		for (int k = 0; k < 2; ++k) {
-			const int xw = lane + 32 * k;
+			const int xw = xw0 + lane + 32 * k;
 			uint32_t r = 0;
-			if (xw < MWS) {
+			if (xw <= xw1) {
 				const uint32_t C = row[xw];
 				const uint32_t P = (xw > 0) ? row[xw - 1] : neutral;
 				const uint32_t N = (xw + 1 < MWS) ? row[xw + 1] : neutral;
@@ -488,23 +490,24 @@ __device__ __forceinline__ void morph_pass_h(uint32_t *img, int H, int MWS) {
 		__syncwarp();
 #pragma unroll
 		for (int k = 0; k < 2; ++k) {
-			const int xw = lane + 32 * k;
-			if (xw < MWS) row[xw] = res[k];
+			const int xw = xw0 + lane + 32 * k;
+			if (xw <= xw1) row[xw] = res[k];
 		}
 	}
 	__syncthreads();
 }
 
 template <int NT, bool IS_MAX>
-__device__ __forceinline__ void morph_pass_v(uint32_t *img, int H, int MWS) {
+__device__ __forceinline__ void morph_pass_v(uint32_t *img, int H, int MWS, int ry0, int ry1, int xw0, int xw1) {
 	// 5x1 along y, in place: a thread owns a vertical segment of one word column; the two rows above
 	// and below the segment are read before anybody writes, then a sliding window runs down it
 	const uint32_t neutral = IS_MAX ? 0u : 0xFFFFFFFFu;
-	const int nseg = max(1, NT / MWS);
-	const int seg_rows = (H + nseg - 1) / nseg;
-	const int xw = threadIdx.x % MWS, seg = threadIdx.x / MWS;
-	const int y0 = seg * seg_rows, y1 = min(H, y0 + seg_rows);
-	const bool active = (seg < nseg) && (y0 < H);
+	const int ncols = xw1 - xw0 + 1, nrows = ry1 - ry0 + 1;
+	const int nseg = max(1, NT / ncols);
+	const int seg_rows = (nrows + nseg - 1) / nseg;
+	const int xw = xw0 + threadIdx.x % ncols, seg = threadIdx.x / ncols;
+	const int y0 = ry0 + seg * seg_rows, y1 = min(ry1 + 1, y0 + seg_rows);
+	const bool active = (seg < nseg) && (y0 <= ry1);
 	auto at = [&](int y) -> uint32_t { return (y >= 0 && y < H) ? img[y * MWS + xw] : neutral; };
 	uint32_t a2 = neutral, a1 = neutral, b1 = neutral, b2 = neutral;
 	if (active) { a2 = at(y0 - 2); a1 = at(y0 - 1); b1 = at(y1); b2 = at(y1 + 1); }
@@ -532,11 +535,11 @@ __device__ __forceinline__ void morph_pass_v(uint32_t *img, int H, int MWS) {
 }
 
 // set the padding bytes (x >= W) of every row to `fill`
-__device__ __forceinline__ void set_row_padding(uint32_t *img, int H, int W, int MWS, uint32_t fill_byte, int NT) {
+__device__ __forceinline__ void set_row_padding(uint32_t *img, int ry0, int ry1, int W, int MWS, uint32_t fill_byte, int NT) {
 	const int first_pad_word = W >> 2;
 	const int pad_words = MWS - first_pad_word;
-	for (int i = threadIdx.x; i < H * pad_words; i += NT) {
-		const int y = i / pad_words, k = i - y * pad_words;
+	for (int i = threadIdx.x; i < (ry1 - ry0 + 1) * pad_words; i += NT) {
+		const int y = ry0 + i / pad_words, k = i % pad_words;
 		const int xw = first_pad_word + k;
 		uint32_t keep_mask = 0u;
 		if (xw == first_pad_word) {
@@ -567,6 +570,7 @@ struct MapScalars {
 	uint32_t rootminw;
 	uint32_t root_edge;
 	int sort_cnt[2];
+	int bb[4];  // bounding box of the kept pixels: ymin, ymax, xmin, xmax
 	unsigned long long sx, sy;
 	uint32_t cnt, tot;
 	uint32_t argmax_key;
@@ -1184,18 +1188,34 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			RVB_PHASE(8);  // EOM + labels + dominant cluster
 			// ---- phase 5: rebuild the map, close it --------------------------------------------------
 			for (int i = tid; i < ln_words; i += NT) img32[i] = 0u;
+			if (tid == 0) { S.bb[0] = 0x7fffffff; S.bb[1] = -1; S.bb[2] = 0x7fffffff; S.bb[3] = -1; }
 			__syncthreads();
-			for (int p = tid; p < n; p += NT) img8[(pts[p] >> 8) * LWPS + (pts[p] & 0xFF)] = val[p];
+			{
+				int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+				for (int p = tid; p < n; p += NT) {
+					const int y = pts[p] >> 8, x = pts[p] & 0xFF;
+					const uint8_t v = val[p];
+					img8[y * LWPS + x] = v;
+					if (v) { ymin = min(ymin, y); ymax = max(ymax, y); xmin = min(xmin, x); xmax = max(xmax, x); }
+				}
+				ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+				xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+				if (lane == 0 && ymax >= 0) {
+					atomicMin(&S.bb[0], ymin); atomicMax(&S.bb[1], ymax); atomicMin(&S.bb[2], xmin); atomicMax(&S.bb[3], xmax);
+				}
+			}
 			__syncthreads();
 			rebuilt = true;
-			if (a.op_close && S.n_clusters > 0) {
-				morph_pass_h<NT, true>(img32, LH, LMWS);
-				morph_pass_v<NT, true>(img32, LH, LMWS);
-				set_row_padding(img32, LH, LW, LMWS, 0xFFu, NT);
+			if (a.op_close && S.n_clusters > 0 && S.bb[1] >= 0) {
+				const int ry0 = max(0, S.bb[0] - 2), ry1 = min(LH - 1, S.bb[1] + 2);
+				const int xw0 = max(0, (S.bb[2] - 2) >> 2), xw1 = min(LMWS - 1, (S.bb[3] + 2) >> 2);
+				morph_pass_h<NT, true>(img32, LH, LMWS, ry0, ry1, xw0, xw1);
+				morph_pass_v<NT, true>(img32, LH, LMWS, ry0, ry1, xw0, xw1);
+				set_row_padding(img32, ry0, ry1, LW, LMWS, 0xFFu, NT);
 				__syncthreads();
-				morph_pass_h<NT, false>(img32, LH, LMWS);
-				morph_pass_v<NT, false>(img32, LH, LMWS);
-				set_row_padding(img32, LH, LW, LMWS, 0x00u, NT);
+				morph_pass_h<NT, false>(img32, LH, LMWS, ry0, ry1, xw0, xw1);
+				morph_pass_v<NT, false>(img32, LH, LMWS, ry0, ry1, xw0, xw1);
+				set_row_padding(img32, ry0, ry1, LW, LMWS, 0x00u, NT);
 				__syncthreads();
 			}
 		}
