@@ -336,6 +336,23 @@ def gpu_arm(args, rank, world, local_rank):
 	# roofline of the dominant kernel (the fused map kernel family): separate un-pipelined pass
 	map_ms, map_launches = timed_map_kernel(args.steps)
 
+	# (i) of SURVEY.md H2: the streaming stages alone (threshold, mean saliency, centroid, track, boxes), i.e. the
+	# same call with the clustering filter switched off -- this is the part of the path that is HBM-bound
+	CP_s = dict(CP)
+	CP_s['clust_filt'] = False
+	params_s = _cabi.params_from_crop_params(CP_s)
+	for _ in range(3):
+		ctx.crop_track_batch(params_s, b_dev)
+	barrier()
+	stream_ms, stream_map_ms = 0.0, 0.0
+	es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	es0.record(streams[0])
+	for _ in range(args.steps):
+		ctx.crop_track_batch(params_s, b_dev)
+		stream_map_ms += ctx.last_map_kernel_ms()[0]
+	es1.record(streams[0])
+	barrier()
+	stream_ms = es0.elapsed_time(es1)
 	if args.phases and rank == 0:
 		ctx.phase_cycles(True)
 		ctx.crop_track_batch(params, b_dev)
@@ -385,6 +402,11 @@ def gpu_arm(args, rank, world, local_rank):
 						'algorithmic_bytes_per_step': algo, 'kernel_ms_per_step': map_ms / args.steps,
 						'kernel_launches_per_step': map_launches / args.steps,
 						'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'},
+			'roofline_streaming_stages': {'what': 'same call with clust_filt=False: threshold, mean saliency, centroid, empty fill, interpolation, low-pass, LOESS, boxes',
+										'bound': 'hbm', 'achieved': NM * ALGO_BYTES_PER_MAP * args.steps / (stream_map_ms / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+										'frac': NM * ALGO_BYTES_PER_MAP * args.steps / (stream_map_ms / 1e3) / 1e9 / peak,
+										'kernel_ms_per_step': stream_map_ms / args.steps, 'ms_per_step': stream_ms / args.steps,
+										'frames_per_sec': frames_per_step * args.steps / (stream_ms / 1e3)},
 			'clocks': clocks,
 		}
 		if cpu_v is not None:

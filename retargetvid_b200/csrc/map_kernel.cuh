@@ -682,6 +682,119 @@ __device__ __forceinline__ void cv_resize_linear_u8(const uint8_t *src, int sH, 
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming variant of the map stage for clust_filt == 0 (smartVidCrop.py:2354: "Skipping clustering"):
+// threshold (a2), raw mean saliency (a3) and centre of mass (a8) are one pass over the map, so there
+// is nothing to keep on chip.  One warp per map, 128-bit loads straight from HBM, SIMD byte compares,
+// dot products for the coordinate sums, five warp reductions, one 96-byte record out.  HBM-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStreamBatch = 9;   // 140 rows x 16 chunks = 2240 chunks = 8.75 per thread: one batch per map
+
+template <bool ARGMAX>
+__global__ void __launch_bounds__(256) map_stream_kernel(const uint8_t *__restrict__ maps, int n_maps, int H, int W, int gstride,
+														  int t_threshold, MapOut *__restrict__ out) {
+	__shared__ uint32_t part[8][5];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// a pixel survives the threshold (and is then non-zero) iff value >= max(t, 1)
+	const uint32_t thr4 = (uint32_t)min(max(t_threshold, 1), 255) * 0x01010101u;
+	const bool none = t_threshold > 255;
+	const int cpr = gstride >> 4;                      // 16-byte chunks per row (gstride is a multiple of 16)
+	const int n_chunks = H * cpr;
+	// thread -> (row offset, chunk in row) is fixed when 256 is a multiple of the chunks per row
+	const bool regular = (256 % cpr) == 0;
+	const int rows_per_iter = regular ? (256 / cpr) : 0;
+	int y_t = regular ? (tid / cpr) : 0;
+	const int xb_t = regular ? ((tid % cpr) << 4) : 0;
+	uint32_t pmask[4];                                 // row padding (x >= W) is the caller's garbage
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int valid = min(max(W - (xb_t + 4 * k), 0), 4);
+		pmask[k] = (valid >= 4) ? 0xFFFFFFFFu : ((valid > 0) ? ((1u << (8 * valid)) - 1u) : 0u);
+	}
+	// one CTA per map (persistent, static stride): 256 threads x 16 B keep the whole map in flight
+	for (int m = blockIdx.x; m < n_maps; m += gridDim.x) {
+		const int4 *src = reinterpret_cast<const int4 *>(maps + (size_t)m * H * gstride);
+		uint32_t raw = 0, cnt = 0, sx = 0, sy = 0, amax = 0;
+		int y = y_t;
+		for (int c0 = tid; c0 < n_chunks; c0 += 256 * kStreamBatch) {
+			// issue a whole batch of 128-bit loads before touching any of them
+			int4 qb[kStreamBatch];
+#pragma unroll
+			for (int j = 0; j < kStreamBatch; ++j) {
+				const int c = c0 + 256 * j;
+				qb[j] = (c < n_chunks) ? __ldcs(src + c) : make_int4(0, 0, 0, 0);   // streamed once: evict-first
+			}
+#pragma unroll
+			for (int j = 0; j < kStreamBatch; ++j) {
+				const int c = c0 + 256 * j;
+				const int4 q = qb[j];
+				int xb = xb_t;
+				uint32_t m4[4] = {pmask[0], pmask[1], pmask[2], pmask[3]};
+				if (!regular) {
+					y = c / cpr;
+					xb = (c - y * cpr) << 4;
+#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						const int valid = min(max(W - (xb + 4 * k), 0), 4);
+						m4[k] = (valid >= 4) ? 0xFFFFFFFFu : ((valid > 0) ? ((1u << (8 * valid)) - 1u) : 0u);
+					}
+				}
+				const uint32_t w4[4] = {(uint32_t)q.x & m4[0], (uint32_t)q.y & m4[1], (uint32_t)q.z & m4[2], (uint32_t)q.w & m4[3]};
+				uint32_t c4 = 0, xl = 0;
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					raw += __vsadu4(w4[k], 0u);
+					const uint32_t nz = none ? 0u : (__vcmpgeu4(w4[k], thr4) & 0x01010101u);
+					c4 = __dp4a(nz, 0x01010101u, c4);
+					xl = __dp4a(nz, 0x03020100u + 0x04040404u * (uint32_t)k, xl);  // x offsets 4k .. 4k+3 inside the chunk
+					if (ARGMAX) {
+#pragma unroll
+						for (int b = 0; b < 4; ++b) {
+							const uint32_t bv = (w4[k] >> (8 * b)) & 0xFFu;
+							if ((nz >> (8 * b)) & 1u) amax = max(amax, (bv << 20) | (0xFFFFFu - (uint32_t)(y * W + xb + 4 * k + b)));
+						}
+					}
+				}
+				cnt += c4;
+				sx += (uint32_t)xb * c4 + xl;
+				sy += (uint32_t)y * c4;
+				y += rows_per_iter;
+			}
+		}
+		raw = __reduce_add_sync(0xffffffffu, raw);
+		cnt = __reduce_add_sync(0xffffffffu, cnt);
+		sx = __reduce_add_sync(0xffffffffu, sx);
+		sy = __reduce_add_sync(0xffffffffu, sy);
+		if (ARGMAX) amax = __reduce_max_sync(0xffffffffu, amax);
+		__syncthreads();  // the previous map's partials have been consumed
+		if (lane == 0) { part[warp][0] = raw; part[warp][1] = cnt; part[warp][2] = sx; part[warp][3] = sy; part[warp][4] = amax; }
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t v[5];
+#pragma unroll
+			for (int k = 0; k < 5; ++k) v[k] = (lane < 8) ? part[lane][k] : 0u;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) v[k] = __reduce_add_sync(0xffffffffu, v[k]);
+			v[4] = __reduce_max_sync(0xffffffffu, v[4]);
+			if (lane == 0) {
+				MapOut r;
+				r.cx = 0.0; r.cy = 0.0; r.raw_sum = v[0]; r.n_points = (int)v[1]; r.n_clusters = -1; r.kept_points = (int)v[1];
+				r.flags = 0; r.pad = 0;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) r.cvrg[k] = 0.0;
+				if (v[1] == 0u) r.flags = kFlagEmpty;
+				else if (!ARGMAX) { r.cx = (double)v[2] / (double)v[1]; r.cy = (double)v[3] / (double)v[1]; }
+				else {
+					const uint32_t lin = 0xFFFFFu - (v[4] & 0xFFFFFu);
+					r.cx = (double)(lin % (uint32_t)W);
+					r.cy = (double)(lin / (uint32_t)W);
+				}
+				out[m] = r;
+			}
+		}
+	}
+}
+
 // resident CTAs per SM the register budget must allow, per capacity class (shared memory bounds the same)
 template <int NT, int TPT>
 struct MapKernelCfg { static constexpr int kMinBlocks = (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1; };

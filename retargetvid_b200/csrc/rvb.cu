@@ -700,30 +700,44 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
 	c->map_launches = 0;
 	CU(cudaEventRecord(c->ev_map0, st));
+	const bool streaming = !p->clust_filt && !rzs.on && !p->exit_on_low_cvrg && !keep_all_maps && d_u8 != nullptr &&
+						   (gstride % 16) == 0 && (((uintptr_t)d_u8) & 15) == 0;
+	if (streaming) {
+		// clustering switched off: one streaming pass, one CTA per map (persistent grid, whole waves)
+		int per_sm = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_stream_kernel<false>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+		const int blocks = std::min(NM, c->n_sm * per_sm);
+		if (p->com_km) map_stream_kernel<false><<<blocks, 256, 0, st>>>(d_u8, NM, H, W, gstride, p->t_threshold, (MapOut *)c->mapout.p);
+		else map_stream_kernel<true><<<blocks, 256, 0, st>>>(d_u8, NM, H, W, gstride, p->t_threshold, (MapOut *)c->mapout.p);
+		CU(cudaGetLastError());
+		c->launches += 1;
+		c->map_launches += 1;
+	} else {
 	// failed / never-reached maps must not look valid
-	CU(cudaMemsetAsync(c->mapout.p, 0xFF, (size_t)NM * sizeof(MapOut), st));
-	{
-		const int nw = (int)work.size();
-		int *cnt = d_cnt;
-		// capacity classes 1536 / 2048 / 3072 / 4096 / 8192 salient pixels (shared memory per CTA grows with
-		// the capacity, so smaller classes keep more maps in flight per SM): a map that does not fit is
-		// appended to the next class's list by the kernel itself (no host round trip)
-		int *ovf[4] = {(int *)(M + o_ovf1), (int *)(M + o_ovf2), (int *)(M + o_ovf3), (int *)(M + o_ovf4)};
-		const int mcs = p->hdbscan_min;
-		for (int k = 0; k < 5; ++k) {
-			a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
-			a.head = cnt + 2 * k;
-			a.list_len = cnt + 2 * k + 1;
-			// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
-			a.ovf_list = (k < 4) ? ovf[k] : nullptr;
-			a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
-			int rc = RVB_OK;
-			if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nw));
-			if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nw));
-			if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nw));
-			if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nw));
-			if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nw));
-			if (rc) return rc;
+		CU(cudaMemsetAsync(c->mapout.p, 0xFF, (size_t)NM * sizeof(MapOut), st));
+		{
+			const int nw = (int)work.size();
+			int *cnt = d_cnt;
+			// capacity classes 1536 / 2048 / 3072 / 4096 / 8192 salient pixels (shared memory per CTA grows with
+			// the capacity, so smaller classes keep more maps in flight per SM): a map that does not fit is
+			// appended to the next class's list by the kernel itself (no host round trip)
+			int *ovf[4] = {(int *)(M + o_ovf1), (int *)(M + o_ovf2), (int *)(M + o_ovf3), (int *)(M + o_ovf4)};
+			const int mcs = p->hdbscan_min;
+			for (int k = 0; k < 5; ++k) {
+				a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
+				a.head = cnt + 2 * k;
+				a.list_len = cnt + 2 * k + 1;
+				// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
+				a.ovf_list = (k < 4) ? ovf[k] : nullptr;
+				a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
+				int rc = RVB_OK;
+				if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nw));
+				if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nw));
+				if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nw));
+				if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nw));
+				if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nw));
+				if (rc) return rc;
+			}
 		}
 	}
 	CU(cudaEventRecord(c->ev_map1, st));

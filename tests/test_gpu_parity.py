@@ -472,3 +472,24 @@ def test_ragged_batch_and_tiny_clips(engine):
 		want = sc_oracle.smart_vid_crop_oracle(vd, CP)
 		assert r.status == 0
 		assert np.array_equal(r.boxes[0], np.array(want['bbs'], dtype=np.int32))
+
+
+def test_streaming_kernel_clust_filt_off(engine):
+	"""clust_filt=False (smartVidCrop.py:2354): the one-warp-per-map streaming kernel equals the fused kernel
+	(taken when filtered maps are requested) and the oracle, for the centroid and the argmax variant."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vds = [synth.make_clip(9300 + i, fc=70 + 9 * i, shot_starts=[33] if i % 2 else []) for i in range(4)]
+	vds.append(synth.make_clip(9310, fc=40, kind='few_points'))
+	for com_km in (True, False):
+		CP = svc.sc_init_crop_params()
+		CP.update(dict(clust_filt=False, com_km=com_km, out_ratio='4:5'))
+		fast = engine.run(vds, CP, ['4:5'], detail=True)
+		slow = engine.run(vds, CP, ['4:5'], detail=True, want_filtered=True)
+		for vd, a, b in zip(vds, fast, slow):
+			assert np.array_equal(a.boxes, b.boxes) and np.array_equal(a.dx, b.dx) and np.array_equal(a.map_scores, b.map_scores)
+			assert np.array_equal(a.map_info[:, 0], b.map_info[:, 0])
+			want = sc_oracle.smart_vid_crop_oracle(vd, CP)
+			assert np.array_equal(a.boxes[0], np.array(want['bbs'], dtype=np.int32))
+			assert np.allclose(a.map_scores, want['mean_sal_scores'], rtol=0, atol=1e-12)
