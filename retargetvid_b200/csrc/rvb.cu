@@ -488,6 +488,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	std::vector<FilterCoef> coefs;
 	std::vector<double> coef_fr;
 	long long scratch_doubles = 0;
+	long long max_spline_doubles = 0, max_lp_doubles = 0;
 	int n_slots = 0;
 	const bool want_filtered = b->filtered_maps != nullptr;
 	const bool keep_all_maps = want_filtered || p->focus_stability;  // focus stability samples every filtered map
@@ -512,6 +513,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 			sh.map_base = d.map_offset + sh.m0;
 			const int n = sh.m1 - sh.m0 + 1, clen = sh.f1 - sh.f0 + 1;
 			const long long need = std::max<long long>(8LL * n + 3, 2LL * (clen + 6 * (RVB_MAX_LP_ORDER + 1)));
+			max_spline_doubles = std::max<long long>(max_spline_doubles, n > 6 ? 8LL * n + 3 : 0);
+			max_lp_doubles = std::max<long long>(max_lp_doubles, clen + 6LL * (RVB_MAX_LP_ORDER + 1));
 			sh.scratch_base = (int)scratch_doubles;
 			scratch_doubles += need;
 			for (int f = sh.f0; f <= sh.f1; ++f) frame_shot[d.frame_offset + f] = d.shot_offset + s;
@@ -773,10 +776,12 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		const cudaMemcpyKind knf = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
 		if (p->focus_stability) CU(cudaMemcpyAsync(b->centres_nf + 2 * (size_t)NM, d_jumps, (size_t)NM * sizeof(double), knf, st));
 	}
-	spline_setup_kernel<<<(NS + 63) / 64, 64, 0, st>>>(d_shots, NS, d_ti, d_dx, d_dy, d_scratch);
+	const int sp_doubles = (int)std::min<long long>(max_spline_doubles, 6144);   // up to 48 KB of shared memory per warp
+	spline_setup_kernel<<<NS, 32, (size_t)sp_doubles * sizeof(double), st>>>(d_shots, NS, d_ti, d_dx, d_dy, d_scratch, sp_doubles);
 	interp_eval_kernel<<<(NF + 255) / 256, 256, 0, st>>>(d_shots, d_fshot, NF, d_ti, d_dx, d_dy, d_scratch, d_dxi, d_dyi);
-	lowpass_kernel<<<(2 * NS + 63) / 64, 64, 0, st>>>(d_shots, NS, d_clips, (const FilterCoef *)(M + o_coefs),
-													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt);
+	const int lp_doubles = (int)std::min<long long>(max_lp_doubles, 6144);
+	lowpass_kernel<<<2 * NS, 32, (size_t)lp_doubles * sizeof(double), st>>>(d_shots, NS, d_clips, (const FilterCoef *)(M + o_coefs),
+													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt, lp_doubles);
 	{
 		const long long warps = 2LL * NF;
 		const int blocks = (int)((warps * 32 + 255) / 256);
@@ -1011,9 +1016,10 @@ extern "C" int rvb_debug_smooth_series(rvb_ctx *c, const rvb_params *p, const do
 	uint8_t *D = (uint8_t *)c->misc.p;
 	CU(cudaMemcpyAsync(D, sg.bytes.data(), sg.bytes.size(), cudaMemcpyHostToDevice, st));
 	CU(cudaStreamSynchronize(st));
-	lowpass_kernel<<<1, 64, 0, st>>>((const ShotDev *)(D + o_sh), 1, (const ClipDev *)(D + o_cl), (const FilterCoef *)(D + o_fc),
+	const int dbg_lp_doubles = std::min(n + 6 * (RVB_MAX_LP_ORDER + 1), 6144);
+	lowpass_kernel<<<2, 32, (size_t)dbg_lp_doubles * sizeof(double), st>>>((const ShotDev *)(D + o_sh), 1, (const ClipDev *)(D + o_cl), (const FilterCoef *)(D + o_fc),
 									  (const int *)(D + o_cc), (const double *)(D + o_x), (const double *)(D + o_y),
-									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt);
+									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt, dbg_lp_doubles);
 	const int blocks = (int)((2LL * n * 32 + 255) / 256);
 	smooth_kernel<<<blocks, 256, 0, st>>>((const ShotDev *)(D + o_sh), (const int *)(D + o_fs), n, (const ClipDev *)(D + o_cl),
 										  (const double *)(D + o_xl), (const double *)(D + o_yl), (double *)(D + o_xs),

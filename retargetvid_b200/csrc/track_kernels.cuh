@@ -193,26 +193,35 @@ __device__ __forceinline__ int bspl_interval(const double *t, int nc, double x) 
 	return lo;
 }
 
-// one thread per shot: build knots and solve the collocation system for x and y together
-__global__ void spline_setup_kernel(const ShotDev *shots, int n_shots, const int *true_inds, const double *dx,
-									const double *dy, double *scratch) {
-	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per shot: build knots and collocation rows (lanes in parallel), solve for x and y together
+// (lane 0, sequential banded elimination).  The working set lives in shared memory when it fits
+// (smem_doubles), otherwise in the shot's global scratch area; knots and coefficients always end up there.
+__global__ void __launch_bounds__(32) spline_setup_kernel(const ShotDev *shots, int n_shots, const int *true_inds,
+														   const double *dx, const double *dy, double *scratch, int smem_doubles) {
+	extern __shared__ double sp_smem[];
+	const int s = blockIdx.x, lane = threadIdx.x;
 	if (s >= n_shots) return;
 	const ShotDev sh = shots[s];
 	const int n = sh.m1 - sh.m0 + 1;
 	if (n <= 6) return;
-	// scratch: t[n+3], cx[n], cy[n], band[n][5]
-	double *t = scratch + sh.scratch_base;
+	// layout: t[n+3], cx[n], cy[n], band[n][5]
+	double *g = scratch + sh.scratch_base;
+	const bool on_chip = (8 * n + 3) <= smem_doubles;
+	double *t = on_chip ? sp_smem : g;
 	double *cx = t + (n + 3);
 	double *cy = cx + n;
 	double *band = cy + n;
 	const int *ti = true_inds + sh.map_base;
-	const double x0 = 0.0;
 	auto X = [&](int i) { return (double)(ti[i] - ti[0]); };
-	t[0] = t[1] = t[2] = x0;
-	for (int i = 1; i <= n - 3; ++i) t[2 + i] = (X(i) + X(i + 1)) / 2.0;
-	t[n] = t[n + 1] = t[n + 2] = X(n - 1);
-	for (int i = 0; i < n; ++i) {
+	for (int i = lane; i < n + 3; i += 32) {
+		double v;
+		if (i < 3) v = 0.0;
+		else if (i >= n) v = X(n - 1);
+		else v = (X(i - 2) + X(i - 1)) / 2.0;   // t[2 + k] = (x_k + x_{k+1}) / 2 for k = 1 .. n-3
+		t[i] = v;
+	}
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) {
 		for (int k = 0; k < 5; ++k) band[i * 5 + k] = 0.0;
 		const double x = X(i);
 		const int mu = bspl_interval(t, n, x);
@@ -227,30 +236,36 @@ __global__ void spline_setup_kernel(const ShotDev *shots, int n_shots, const int
 		cx[i] = dx[sh.map_base + i];
 		cy[i] = dy[sh.map_base + i];
 	}
-	// Gaussian elimination without pivoting (the collocation matrix is totally positive)
-	for (int i = 0; i < n; ++i) {
-		const double piv = band[i * 5 + 2];
-		for (int r = i + 1; r <= min(n - 1, i + 2); ++r) {
-			const int o = i - r + 2;  // column i in row r
-			const double f = band[r * 5 + o] / piv;
-			if (f == 0.0) continue;
-			for (int c = i; c <= min(n - 1, i + 2); ++c) {
-				const int oi = c - i + 2, orr = c - r + 2;
-				if (orr >= 0 && orr < 5) band[r * 5 + orr] -= f * band[i * 5 + oi];
+	__syncwarp();
+	if (lane == 0) {
+		// Gaussian elimination without pivoting (the collocation matrix is totally positive)
+		for (int i = 0; i < n; ++i) {
+			const double piv = band[i * 5 + 2];
+			for (int r = i + 1; r <= min(n - 1, i + 2); ++r) {
+				const int o = i - r + 2;  // column i in row r
+				const double f = band[r * 5 + o] / piv;
+				if (f == 0.0) continue;
+				for (int c = i; c <= min(n - 1, i + 2); ++c) {
+					const int oi = c - i + 2, orr = c - r + 2;
+					if (orr >= 0 && orr < 5) band[r * 5 + orr] -= f * band[i * 5 + oi];
+				}
+				cx[r] -= f * cx[i];
+				cy[r] -= f * cy[i];
 			}
-			cx[r] -= f * cx[i];
-			cy[r] -= f * cy[i];
+		}
+		for (int i = n - 1; i >= 0; --i) {
+			double sx = cx[i], sy = cy[i];
+			for (int c = i + 1; c <= min(n - 1, i + 2); ++c) {
+				sx -= band[i * 5 + (c - i + 2)] * cx[c];
+				sy -= band[i * 5 + (c - i + 2)] * cy[c];
+			}
+			cx[i] = sx / band[i * 5 + 2];
+			cy[i] = sy / band[i * 5 + 2];
 		}
 	}
-	for (int i = n - 1; i >= 0; --i) {
-		double sx = cx[i], sy = cy[i];
-		for (int c = i + 1; c <= min(n - 1, i + 2); ++c) {
-			sx -= band[i * 5 + (c - i + 2)] * cx[c];
-			sy -= band[i * 5 + (c - i + 2)] * cy[c];
-		}
-		cx[i] = sx / band[i * 5 + 2];
-		cy[i] = sy / band[i * 5 + 2];
-	}
+	__syncwarp();
+	if (on_chip)
+		for (int i = lane; i < 3 * n + 3; i += 32) g[i] = t[i];   // knots + both coefficient vectors
 }
 
 // one thread per (shot-local frame): evaluate the interpolant
@@ -311,10 +326,11 @@ __device__ __forceinline__ double df2t_step(const FilterCoef &fc, double *z, dou
 	return y;
 }
 
-__global__ void lowpass_kernel(const ShotDev *shots, int n_shots, const ClipDev *clips, const FilterCoef *coefs,
-							   const int *clip_coef, const double *dxi, const double *dyi, double *dxl, double *dyl,
-							   double *scratch, int lp_filt) {
-	const int id = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n_shots, const ClipDev *clips, const FilterCoef *coefs,
+													  const int *clip_coef, const double *dxi, const double *dyi, double *dxl, double *dyl,
+													  double *scratch, int lp_filt, int smem_doubles) {
+	extern __shared__ double lp_smem[];
+	const int id = blockIdx.x, lane = threadIdx.x;
 	if (id >= n_shots * 2) return;
 	const int s = id >> 1, axis = id & 1;
 	const ShotDev sh = shots[s];
@@ -322,38 +338,42 @@ __global__ void lowpass_kernel(const ShotDev *shots, int n_shots, const ClipDev 
 	const double *x = (axis ? dyi : dxi) + sh.frame_base;
 	double *out = (axis ? dyl : dxl) + sh.frame_base;
 	if (!lp_filt) {
-		for (int i = 0; i < cl; ++i) out[i] = x[i];
+		for (int i = lane; i < cl; i += 32) out[i] = x[i];
 		return;
 	}
 	const FilterCoef &fc = coefs[clip_coef[sh.clip]];
 	const int m = fc.order;
 	const int edge = 3 * (m + 1);
 	if (m > 0 && cl > edge) {
-		// forward pass over the odd extension, stored in scratch, then backward pass
-		double *buf = scratch + sh.scratch_base + (size_t)axis * (cl + 2 * edge);
+		// odd extension (lanes in parallel), forward pass in place, backward pass in place (lane 0), copy out
 		const int ne = cl + 2 * edge;
-		auto ext = [&](int i) -> double {
-			if (i < edge) return 2.0 * x[0] - x[edge - i];
-			if (i < edge + cl) return x[i - edge];
-			return 2.0 * x[cl - 1] - x[cl - 2 - (i - edge - cl)];
-		};
-		double z[RVB_MAX_LP_ORDER];
-		const double e0 = ext(0);
-		for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * e0;
-		for (int i = 0; i < ne; ++i) buf[i] = df2t_step(fc, z, ext(i));
-		const double y0 = buf[ne - 1];
-		for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * y0;
-		for (int i = ne - 1; i >= 0; --i) {
-			const double y = df2t_step(fc, z, buf[i]);
-			if (i >= edge && i < edge + cl) out[i - edge] = y;
+		double *buf = (ne <= smem_doubles) ? lp_smem : (scratch + sh.scratch_base + (size_t)axis * ne);
+		for (int i = lane; i < ne; i += 32) {
+			double v;
+			if (i < edge) v = 2.0 * x[0] - x[edge - i];
+			else if (i < edge + cl) v = x[i - edge];
+			else v = 2.0 * x[cl - 1] - x[cl - 2 - (i - edge - cl)];
+			buf[i] = v;
 		}
+		__syncwarp();
+		if (lane == 0) {
+			double z[RVB_MAX_LP_ORDER];
+			const double e0 = buf[0];
+			for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * e0;
+			for (int i = 0; i < ne; ++i) buf[i] = df2t_step(fc, z, buf[i]);
+			const double y0 = buf[ne - 1];
+			for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * y0;
+			for (int i = ne - 1; i >= 0; --i) buf[i] = df2t_step(fc, z, buf[i]);
+		}
+		__syncwarp();
+		for (int i = lane; i < cl; i += 32) out[i] = buf[edge + i];
 		return;
 	}
 	// fallback: 5-tap moving average of the interior, edges untouched (smartVidCrop.py:1611-1615)
-	for (int i = 0; i < cl; ++i) out[i] = x[i];
-	if (cl >= 5) {
-		for (int i = 2; i < cl - 2; ++i)
-			out[i] = ((((x[i - 2] + x[i - 1]) + x[i]) + x[i + 1]) + x[i + 2]) / 5.0;
+	for (int i = lane; i < cl; i += 32) {
+		double v = x[i];
+		if (cl >= 5 && i >= 2 && i < cl - 2) v = ((((x[i - 2] + x[i - 1]) + x[i]) + x[i + 1]) + x[i + 2]) / 5.0;
+		out[i] = v;
 	}
 }
 
