@@ -586,37 +586,53 @@ struct MapScalars {
 	} while (0)
 
 // ---------------------------------------------------------------------------------------------
-// Prim on the mutual-reachability graph, all pairs, K points per thread in registers (K is the exact
-// number of occupied slots, so the unrolled update carries no per-slot predicate).  From point 0,
-// lowest index wins ties (np.argmin) -- _linkage.pyx:97-112.  key = (min reachability << 13) | index;
-// |dx|,|dy| by one VABSDIFF4, dx^2+dy^2 by one IDP.4A, max(d2, core_j, core_u) by one VIMNMX3.
+// Prim on the mutual-reachability graph, all pairs.  From point 0, lowest index wins ties (np.argmin) --
+// _linkage.pyx:97-112.  key = (min reachability << 13) | index; |dx|,|dy| by one VABSDIFF4, dx^2+dy^2 by
+// one IDP.4A, max(d2, core_j, core_u) by one VIMNMX3, one redux + one __syncthreads per added node.
+//
+// The points OUTSIDE the tree live in registers, K per thread; the run is cut into segments: whenever
+// the live points fit into K-1 slots per thread they are compacted through shared memory (their keys
+// carry the index) and the next segment runs a loop specialised for K-1 slots, so no instruction is
+// spent on points already in the tree and the unrolled update carries no per-slot predicate.
 // ---------------------------------------------------------------------------------------------
+struct PrimState {
+	int step;      // edges found so far
+	int live;      // points outside the tree
+	int cur;       // the node added last (its update has not been applied yet)
+};
+
 template <int NT, int K>
-__device__ __forceinline__ void prim_all_pairs(const uint16_t *pts, const uint32_t *core, uint16_t *order, uint32_t *wp,
-												uint32_t (*wmin)[32], int n) {
+__device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t *core, uint16_t *order, uint32_t *wp,
+											  uint32_t (*wmin)[32], const uint32_t *lkey_in, uint32_t *lkey_out, uint16_t *slot_of,
+											  int *live_cnt, PrimState &st, int nsteps, bool write_back) {
 	constexpr int NW = NT / 32;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t pxy[K], pc[K], key[K], idc[K];
 #pragma unroll
 	for (int i = 0; i < K; ++i) {
-		const int j = tid + i * NT;
-		idc[i] = (uint32_t)j;
-		if (j < n) {
+		const int pos = tid + i * NT;
+		if (pos < st.live) {
+			const uint32_t k = lkey_in[pos];
+			const uint32_t j = k & kKeyIdxMask;
+			key[i] = k;
+			idc[i] = j;
 			pxy[i] = pts[j];
 			pc[i] = core[j];
+			slot_of[j] = (uint16_t)(tid | (i << 10));
 		} else {
-			pxy[i] = 0;
+			key[i] = 0xFFFFFFFFu;
+			idc[i] = 0u;
+			pxy[i] = 0u;
 			pc[i] = kInTreeCore;
 		}
-		key[i] = 0xFFFFFFFFu;
 	}
-	if (tid == 0) {
-		pc[0] = kInTreeCore;  // point 0 starts the tree
-		order[0] = 0;
-	}
-	uint32_t cxy = pts[0];
-	uint32_t cc = core[0];
-	for (int step = 0; step < n - 1; ++step) {
+	if (tid == 0) *live_cnt = 0;
+	__syncthreads();
+	int cur = st.cur;
+	uint32_t cxy = pts[cur];
+	uint32_t cc = core[cur];
+	const int step_end = st.step + nsteps;
+	for (int step = st.step; step < step_end; ++step) {
 		uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
 		for (int i = 0; i < K; ++i) {
@@ -634,31 +650,47 @@ __device__ __forceinline__ void prim_all_pairs(const uint16_t *pts, const uint32
 		__syncthreads();
 		uint32_t g = (lane < NW) ? wm[lane] : 0xFFFFFFFFu;
 		g = __reduce_min_sync(0xffffffffu, g);
-		const int nj = (int)(g & kKeyIdxMask);
+		cur = (int)(g & kKeyIdxMask);
 		if (tid == 0) {
-			order[step + 1] = (uint16_t)nj;
+			order[step + 1] = (uint16_t)cur;
 			wp[step] = g >> kKeyShift;
 		}
 		// the owner retires the new node
-		if ((nj % NT) == tid) {
-			const int slot = nj / NT;
+		const uint32_t so = slot_of[cur];
+		if ((int)(so & 0x3FFu) == tid) {
+			const int slot = (int)(so >> 10);
 #pragma unroll
 			for (int i = 0; i < K; ++i)
 				if (i == slot) { pc[i] = kInTreeCore; key[i] = 0xFFFFFFFFu; }
 		}
-		cxy = pts[nj];
-		cc = core[nj];
+		cxy = pts[cur];
+		cc = core[cur];
 	}
+	if (write_back) {
+		// hand the live points (key carries the index) to the next segment, in any order
+#pragma unroll
+		for (int i = 0; i < K; ++i) {
+			if (pc[i] != kInTreeCore) {
+				const int p = atomicAdd(live_cnt, 1);
+				lkey_out[p] = key[i];
+			}
+		}
+	}
+	st.step = step_end;
+	st.live -= nsteps;
+	st.cur = cur;
+	__syncthreads();
 }
 
 template <int NT, int TPT, int K = 1>
-__device__ __forceinline__ void prim_dispatch(int ncnt, const uint16_t *pts, const uint32_t *core, uint16_t *order,
-											   uint32_t *wp, uint32_t (*wmin)[32], int n) {
+__device__ __forceinline__ void prim_dispatch(int ncnt, const uint16_t *pts, const uint32_t *core, uint16_t *order, uint32_t *wp,
+											   uint32_t (*wmin)[32], const uint32_t *lin, uint32_t *lout, uint16_t *slot_of, int *live_cnt,
+											   PrimState &st, int nsteps, bool write_back) {
 	if constexpr (K >= TPT) {
-		prim_all_pairs<NT, TPT>(pts, core, order, wp, wmin, n);
+		prim_segment<NT, TPT>(pts, core, order, wp, wmin, lin, lout, slot_of, live_cnt, st, nsteps, write_back);
 	} else {
-		if (ncnt <= K) prim_all_pairs<NT, K>(pts, core, order, wp, wmin, n);
-		else prim_dispatch<NT, TPT, K + 1>(ncnt, pts, core, order, wp, wmin, n);
+		if (ncnt <= K) prim_segment<NT, K>(pts, core, order, wp, wmin, lin, lout, slot_of, live_cnt, st, nsteps, write_back);
+		else prim_dispatch<NT, TPT, K + 1>(ncnt, pts, core, order, wp, wmin, lin, lout, slot_of, live_cnt, st, nsteps, write_back);
 	}
 }
 
@@ -1102,9 +1134,31 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 
 			RVB_PHASE(2);  // core distances
 			// ---- phase 3: Prim on the mutual-reachability graph -------------------------------------
-			// (prim_all_pairs above; specialised on the number of occupied register slots)
-			static_assert(kKeyShift == 13, "prim_all_pairs multiplies by 8192");
-			prim_dispatch<NT, TPT>((n + NT - 1) / NT, pts, core, order, wp, S.wmin, n);
+			// (prim_segment above: live points in registers, compacted whenever a slot per thread frees up)
+			static_assert(kKeyShift == 13, "prim_segment multiplies by 8192");
+			{
+				// live-key lists in the storage the sort and the tree use later: A = d4, B = rank + pe, slot_of = pl
+				uint32_t *lkA = skey;
+				uint32_t *lkB = reinterpret_cast<uint32_t *>(rank);
+				uint16_t *slot_of = pl;
+				// every point but the root, "not reached yet": the largest weight field, index in the low bits
+				for (int j = tid + 1; j < n; j += NT) lkA[j - 1] = 0xFFFFE000u | (uint32_t)j;
+				if (tid == 0) order[0] = 0;
+				__syncthreads();
+				PrimState ps;
+				ps.step = 0; ps.live = n - 1; ps.cur = 0;
+				int flip = 0;
+				while (ps.step < n - 1) {
+					const int kslots = (ps.live + NT - 1) / NT;
+					// run until the live points fit into one slot less per thread (or to the end)
+					int nsteps = (kslots > 1) ? (ps.live - (kslots - 1) * NT) : ps.live;
+					nsteps = min(nsteps, n - 1 - ps.step);
+					const bool more = (ps.step + nsteps) < (n - 1);
+					prim_dispatch<NT, TPT>(kslots, pts, core, order, wp, S.wmin, flip ? lkB : lkA, flip ? lkA : lkB, slot_of,
+										   &S.sort_cnt[0], ps, nsteps, more);
+					flip ^= 1;
+				}
+			}
 			__syncthreads();
 
 			RVB_PHASE(3);  // Prim
