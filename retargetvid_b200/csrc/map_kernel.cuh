@@ -153,6 +153,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 				 ::"r"(smem_u32addr(dst)), "l"(src), "r"(bytes), "r"(smem_u32addr(bar)) : "memory");
 }
 
+// shared-memory accesses through precomputed 32-bit addresses (the hot Prim loop must not rebuild generic pointers)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 template <int NT>
 __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch /*[32]*/) {
 	v = __reduce_add_sync(0xffffffffu, v);
@@ -632,6 +646,10 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 	uint32_t cxy = pts[cur];
 	uint32_t cc = core[cur];
 	const int step_end = st.step + nsteps;
+	// 32-bit shared addresses, computed once
+	const uint32_t a_pts = smem_u32addr(pts), a_core = smem_u32addr(core), a_order = smem_u32addr(order), a_wp = smem_u32addr(wp);
+	const uint32_t a_slot = smem_u32addr(slot_of), a_wm = smem_u32addr(&wmin[0][0]);
+	const uint32_t a_wm_mine = a_wm + 4u * (uint32_t)warp, a_wm_lane = a_wm + 4u * (uint32_t)min(lane, NW - 1);
 	for (int step = st.step; step < step_end; ++step) {
 		uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
@@ -645,26 +663,28 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 			best = min(best, key[i]);
 		}
 		best = __reduce_min_sync(0xffffffffu, best);
-		uint32_t *wm = wmin[step & 1];
-		if (lane == 0) wm[warp] = best;
+		const uint32_t par = (uint32_t)(step & 1) * 128u;   // wmin[step & 1]
+		if (lane == 0) sts_u32(a_wm_mine + par, best);
 		__syncthreads();
-		uint32_t g = (lane < NW) ? wm[lane] : 0xFFFFFFFFu;
+		// lanes >= NW re-read the last entry: harmless for a minimum
+		uint32_t g = lds_u32(a_wm_lane + par);
 		g = __reduce_min_sync(0xffffffffu, g);
-		cur = (int)(g & kKeyIdxMask);
+		const uint32_t cu = g & kKeyIdxMask;
+		cur = (int)cu;
 		if (tid == 0) {
-			order[step + 1] = (uint16_t)cur;
-			wp[step] = g >> kKeyShift;
+			sts_u16(a_order + 2u * (uint32_t)(step + 1), cu);
+			sts_u32(a_wp + 4u * (uint32_t)step, g >> kKeyShift);
 		}
 		// the owner retires the new node
-		const uint32_t so = slot_of[cur];
+		const uint32_t so = lds_u16(a_slot + 2u * cu);
+		cxy = lds_u16(a_pts + 2u * cu);
+		cc = lds_u32(a_core + 4u * cu);
 		if ((int)(so & 0x3FFu) == tid) {
 			const int slot = (int)(so >> 10);
 #pragma unroll
 			for (int i = 0; i < K; ++i)
 				if (i == slot) { pc[i] = kInTreeCore; key[i] = 0xFFFFFFFFu; }
 		}
-		cxy = pts[cur];
-		cc = core[cur];
 	}
 	if (write_back) {
 		// hand the live points (key carries the index) to the next segment, in any order
