@@ -664,14 +664,14 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 		}
 		best = __reduce_min_sync(0xffffffffu, best);
 		const uint32_t par = (uint32_t)(step & 1) * 128u;   // wmin[step & 1]
-		if (lane == 0) sts_u32(a_wm_mine + par, best);
+		sts_u32(a_wm_mine + par, best);   // every lane holds the warp minimum: same address, same value, no branch
 		__syncthreads();
 		// lanes >= NW re-read the last entry: harmless for a minimum
 		uint32_t g = lds_u32(a_wm_lane + par);
 		g = __reduce_min_sync(0xffffffffu, g);
 		const uint32_t cu = g & kKeyIdxMask;
 		cur = (int)cu;
-		if (tid == 0) {
+		if (warp == 0) {   // warp-uniform: all lanes store the same values
 			sts_u16(a_order + 2u * (uint32_t)(step + 1), cu);
 			sts_u32(a_wp + 4u * (uint32_t)step, g >> kKeyShift);
 		}
