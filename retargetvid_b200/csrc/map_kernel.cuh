@@ -615,9 +615,11 @@ struct PrimState {
 	int cur;       // the node added last (its update has not been applied yet)
 };
 
+// pinfo[j] = { core_j | slot_code << 17, packed (x, y) }: everything a step needs about the node it just added
+// comes from one 64-bit shared load.  slot_code = owner thread | register slot << 10.
 template <int NT, int K>
-__device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t *core, uint16_t *order, uint32_t *wp,
-											  uint32_t (*wmin)[32], const uint32_t *lkey_in, uint32_t *lkey_out, uint16_t *slot_of,
+__device__ __forceinline__ void prim_segment(uint2 *pinfo, uint16_t *order, uint32_t *wp,
+											  uint32_t (*wmin)[32], const uint32_t *lkey_in, uint32_t *lkey_out,
 											  int *live_cnt, PrimState &st, int nsteps, bool write_back) {
 	constexpr int NW = NT / 32;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -630,9 +632,10 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 			const uint32_t j = k & kKeyIdxMask;
 			key[i] = k;
 			idc[i] = j;
-			pxy[i] = pts[j];
-			pc[i] = core[j];
-			slot_of[j] = (uint16_t)(tid | (i << 10));
+			const uint2 pi = pinfo[j];
+			pxy[i] = pi.y;
+			pc[i] = pi.x & 0x1FFFFu;
+			pinfo[j].x = pc[i] | ((uint32_t)(tid | (i << 10)) << 17);
 		} else {
 			key[i] = 0xFFFFFFFFu;
 			idc[i] = 0u;
@@ -643,12 +646,12 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 	if (tid == 0) *live_cnt = 0;
 	__syncthreads();
 	int cur = st.cur;
-	uint32_t cxy = pts[cur];
-	uint32_t cc = core[cur];
+	uint32_t cxy = pinfo[cur].y;
+	uint32_t cc = pinfo[cur].x & 0x1FFFFu;
 	const int step_end = st.step + nsteps;
 	// 32-bit shared addresses, computed once
-	const uint32_t a_pts = smem_u32addr(pts), a_core = smem_u32addr(core), a_order = smem_u32addr(order), a_wp = smem_u32addr(wp);
-	const uint32_t a_slot = smem_u32addr(slot_of), a_wm = smem_u32addr(&wmin[0][0]);
+	const uint32_t a_info = smem_u32addr(pinfo), a_order = smem_u32addr(order), a_wp = smem_u32addr(wp);
+	const uint32_t a_wm = smem_u32addr(&wmin[0][0]);
 	const uint32_t a_wm_mine = a_wm + 4u * (uint32_t)warp, a_wm_lane = a_wm + 4u * (uint32_t)min(lane, NW - 1);
 	for (int step = st.step; step < step_end; ++step) {
 		uint32_t best = 0xFFFFFFFFu;
@@ -676,9 +679,11 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 			sts_u32(a_wp + 4u * (uint32_t)step, g >> kKeyShift);
 		}
 		// the owner retires the new node
-		const uint32_t so = lds_u16(a_slot + 2u * cu);
-		cxy = lds_u16(a_pts + 2u * cu);
-		cc = lds_u32(a_core + 4u * cu);
+		uint32_t ix, iy;
+		asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ix), "=r"(iy) : "r"(a_info + 8u * cu) : "memory");
+		const uint32_t so = ix >> 17;
+		cxy = iy;
+		cc = ix & 0x1FFFFu;
 		if ((int)(so & 0x3FFu) == tid) {
 			const int slot = (int)(so >> 10);
 #pragma unroll
@@ -703,14 +708,14 @@ __device__ __forceinline__ void prim_segment(const uint16_t *pts, const uint32_t
 }
 
 template <int NT, int TPT, int K = 1>
-__device__ __forceinline__ void prim_dispatch(int ncnt, const uint16_t *pts, const uint32_t *core, uint16_t *order, uint32_t *wp,
-											   uint32_t (*wmin)[32], const uint32_t *lin, uint32_t *lout, uint16_t *slot_of, int *live_cnt,
+__device__ __forceinline__ void prim_dispatch(int ncnt, uint2 *pinfo, uint16_t *order, uint32_t *wp,
+											   uint32_t (*wmin)[32], const uint32_t *lin, uint32_t *lout, int *live_cnt,
 											   PrimState &st, int nsteps, bool write_back) {
 	if constexpr (K >= TPT) {
-		prim_segment<NT, TPT>(pts, core, order, wp, wmin, lin, lout, slot_of, live_cnt, st, nsteps, write_back);
+		prim_segment<NT, TPT>(pinfo, order, wp, wmin, lin, lout, live_cnt, st, nsteps, write_back);
 	} else {
-		if (ncnt <= K) prim_segment<NT, K>(pts, core, order, wp, wmin, lin, lout, slot_of, live_cnt, st, nsteps, write_back);
-		else prim_dispatch<NT, TPT, K + 1>(ncnt, pts, core, order, wp, wmin, lin, lout, slot_of, live_cnt, st, nsteps, write_back);
+		if (ncnt <= K) prim_segment<NT, K>(pinfo, order, wp, wmin, lin, lout, live_cnt, st, nsteps, write_back);
+		else prim_dispatch<NT, TPT, K + 1>(ncnt, pinfo, order, wp, wmin, lin, lout, live_cnt, st, nsteps, write_back);
 	}
 }
 
@@ -1157,10 +1162,13 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			// (prim_segment above: live points in registers, compacted whenever a slot per thread frees up)
 			static_assert(kKeyShift == 13, "prim_segment multiplies by 8192");
 			{
-				// live-key lists in the storage the sort and the tree use later: A = d4, B = rank + pe, slot_of = pl
-				uint32_t *lkA = skey;
-				uint32_t *lkB = reinterpret_cast<uint32_t *>(rank);
-				uint16_t *slot_of = pl;
+				// storage the sort and the tree use later: pinfo = d4 + rank + pe (8 B/point), live-key lists A = a4
+				// (the core distances move into pinfo first), B = pl + queue
+				uint2 *pinfo = reinterpret_cast<uint2 *>(skey);
+				uint32_t *lkA = core;
+				uint32_t *lkB = reinterpret_cast<uint32_t *>(pl);
+				for (int j = tid; j < n; j += NT) pinfo[j] = make_uint2(core[j], (uint32_t)pts[j]);
+				__syncthreads();
 				// every point but the root, "not reached yet": the largest weight field, index in the low bits
 				for (int j = tid + 1; j < n; j += NT) lkA[j - 1] = 0xFFFFE000u | (uint32_t)j;
 				if (tid == 0) order[0] = 0;
@@ -1174,7 +1182,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 					int nsteps = (kslots > 1) ? (ps.live - (kslots - 1) * NT) : ps.live;
 					nsteps = min(nsteps, n - 1 - ps.step);
 					const bool more = (ps.step + nsteps) < (n - 1);
-					prim_dispatch<NT, TPT>(kslots, pts, core, order, wp, S.wmin, flip ? lkB : lkA, flip ? lkA : lkB, slot_of,
+					prim_dispatch<NT, TPT>(kslots, pinfo, order, wp, S.wmin, flip ? lkB : lkA, flip ? lkA : lkB,
 										   &S.sort_cnt[0], ps, nsteps, more);
 					flip ^= 1;
 				}
