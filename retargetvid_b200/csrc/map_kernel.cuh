@@ -865,6 +865,8 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 	constexpr int NW = NT / 32;
 	const int H = a.H, W = a.W, WPS = a.WPS, MWS = WPS >> 2;
 	const int n_words = H * MWS;
+	// rows are usually 64 words (256 bytes): index -> (row, word) without an integer division
+	const int mws_shift = ((MWS & (MWS - 1)) == 0) ? (31 - __clz(MWS)) : -1;
 
 	uint16_t *pts = reinterpret_cast<uint16_t *>(smem + L.pts);
 	uint8_t *val = smem + L.val;
@@ -960,7 +962,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			const int first_pad_word = W >> 2;
 			uint32_t raw = 0, post = 0;
 			for (int i = tid; i < n_words; i += NT) {
-				const int y = i / MWS, xw = i - y * MWS;
+				const int y = (mws_shift >= 0) ? (i >> mws_shift) : (i / MWS), xw = i - y * MWS;
 				uint32_t v = map32[i];
 				if (xw >= first_pad_word) {
 					const int valid = (xw == first_pad_word) ? (W & 3) : 0;
