@@ -118,8 +118,23 @@ struct MapArgs {
 	int rz_dx, rz_dy, rz_ux, rz_uy, rz_nx, rz_ny;   // down x/y: idx,a0,a1 ; up x/y: idx,a0,a1 ; nearest x/y: idx
 	// params
 	int t_threshold, clust_filt, mcs, min_samples, select_sum, op_close, com_km;
+	// split pipeline (front -> prim_kernel -> back): per-point scratch in HBM, addressed by a per-map point offset
+	int *cls_lists;            // front: kSplitClasses lists of cls_stride entries, filled by the front kernel
+	int *cls_cnt;              // front: their lengths
+	int cls_stride;
+	int *scr_off;              // [N] point offset of a map's scratch (front writes, prim/back read)
+	unsigned long long *scr_top;  // bump allocator (points)
+	unsigned int scr_cap;      // points available (< 2^31)
+	uint2 *scr_pinfo;          // {core distance, (y << 8) | x}
+	uint8_t *scr_val;          // pixel values
+	uint32_t *scr_pkey;        // Prim output: (edge weight << 13) | node, in the order the nodes were added
 	SmemLayout lay;
 };
+
+// split pipeline: point-count classes of the Prim / back launches
+constexpr int kSplitClasses = 4;
+__host__ __device__ constexpr int split_class_cap(int k) { return k == 0 ? 768 : k == 1 ? 1536 : k == 2 ? 2048 : 3072; }
+constexpr int kModeMono = 0, kModeFront = 1, kModeBack = 2;
 
 __constant__ RingTable c_rings;
 
@@ -853,11 +868,16 @@ __global__ void __launch_bounds__(256) map_stream_kernel(const uint8_t *__restri
 }
 
 // resident CTAs per SM the register budget must allow, per capacity class (shared memory bounds the same)
-template <int NT, int TPT>
-struct MapKernelCfg { static constexpr int kMinBlocks = (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1; };
+template <int NT, int TPT, int MODE>
+struct MapKernelCfg {
+	static constexpr int kMinBlocks = (MODE == kModeFront) ? 4 : (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1;
+};
 
-template <int NT, int TPT>
-__global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_kernel(const MapArgs a) {
+// MODE kModeMono: the whole path for one map after the other (cut-adjacent chains, the largest classes, resize).
+// MODE kModeFront: load .. core distances, then the points go to HBM scratch and the map to a Prim class list.
+// MODE kModeBack: points and Prim result come back from scratch; sort .. results.
+template <int NT, int TPT, int MODE = kModeMono>
+__global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) map_kernel(const MapArgs a) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ MapScalars S;
 	const SmemLayout &L = a.lay;
@@ -900,6 +920,13 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 #pragma unroll
 		for (int r = 0; r < 8; ++r) res.cvrg[r] = 0.0;
 
+		uint8_t *img8 = map8;
+		uint32_t *img32 = map32;
+		int LH = H, LW = W, LWPS = WPS;
+		int LMWS = LWPS >> 2, ln_words = LH * LMWS;
+		bool rz = false;
+		int n = 0;
+		if constexpr (MODE != kModeBack) {
 		// ---- phase 0: stage the map in shared memory --------------------------------------------
 		if (a.maps_u8 != nullptr) {
 			const uint8_t *src = a.maps_u8 + (size_t)m * H * a.gstride;
@@ -994,10 +1021,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 
 		// ---- resize_factor != 1: the clustering runs on a down-scaled copy (smartVidCrop.py:1078-1084);
 		// an all-zero map is returned untouched (:1064)
-		uint8_t *img8 = map8;
-		uint32_t *img32 = map32;
-		int LH = H, LW = W, LWPS = WPS;
-		const bool rz = a.resize_on && (S.tot != 0u);
+		rz = a.resize_on && (S.tot != 0u);
 		if (rz) {
 			uint8_t *small8 = smem + L.small;
 			for (int i = tid; i < (a.Hs * a.WSs) >> 2; i += NT) reinterpret_cast<uint32_t *>(small8)[i] = 0u;
@@ -1016,11 +1040,10 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			img32 = reinterpret_cast<uint32_t *>(small8);
 			LH = a.Hs; LW = a.Ws; LWPS = a.WSs;
 		}
-		const int LMWS = LWPS >> 2;
-		const int ln_words = LH * LMWS;
+		LMWS = LWPS >> 2;
+		ln_words = LH * LMWS;
 
 		// ---- phase 1: compact the non-zero pixels in row-major order ----------------------------
-		int n;
 		{
 			const int chunk = (ln_words + NT - 1) / NT;
 			const int w0 = tid * chunk, w1 = min(ln_words, w0 + chunk);
@@ -1063,8 +1086,18 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			m = -1;  // a chain continues in the next capacity class, starting with this map
 			continue;
 		}
+		} else {
+			// ---- back half: the front kernel's record and points come back from scratch --------------
+			res = a.out[m];
+			n = res.n_points;
+			const size_t off = (size_t)a.scr_off[m];
+			for (int j = tid; j < n; j += NT) {
+				pts[j] = (uint16_t)a.scr_pinfo[off + j].y;
+				val[j] = a.scr_val[off + j];
+			}
+		}
 
-		const bool do_cluster = a.clust_filt && n > 0 && (n > a.mcs + 1);
+		const bool do_cluster = (MODE == kModeBack) || (a.clust_filt && n > 0 && (n > a.mcs + 1));
 		bool rebuilt = false;
 		if (do_cluster) {
 			uint32_t *core = reinterpret_cast<uint32_t *>(smem + L.a4);
@@ -1093,6 +1126,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			uint16_t *cl_selanc = reinterpret_cast<uint16_t *>(smem + L.cl_selanc);
 			const int MW = (LW + 31) >> 5;
 
+			if constexpr (MODE != kModeBack) {
 			// ---- phase 2: core distances on the lattice -------------------------------------------
 			// k-th nearest OTHER salient pixel (hdbscan: sorted-row index min_samples, self at 0).
 			int kk = (a.min_samples > 0) ? a.min_samples : a.mcs;
@@ -1160,10 +1194,52 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT>::kMinBlocks) map_ker
 			}
 
 			RVB_PHASE(2);  // core distances
+			}
+			if constexpr (MODE == kModeFront) {
+				// ---- front half ends here: the points go to scratch, the map to the Prim list of its size class
+				if (tid == 0) {
+					const unsigned long long need = (unsigned long long)((n + 15) & ~15);
+					const unsigned long long off = atomicAdd(a.scr_top, need);
+					S.fb_count = (off + need <= (unsigned long long)a.scr_cap) ? (int)off : -1;
+				}
+				__syncthreads();
+				const int off = S.fb_count;
+				if (off < 0) {
+					// scratch exhausted: a monolithic launch takes the map
+					if (tid == 0) {
+						const int k = atomicAdd(a.ovf_len, 1);
+						a.ovf_list[k] = m;
+					}
+				} else {
+					for (int j = tid; j < n; j += NT) {
+						a.scr_pinfo[(size_t)off + j] = make_uint2(core[j], (uint32_t)pts[j]);
+						a.scr_val[(size_t)off + j] = val[j];
+					}
+					if (tid == 0) {
+						a.scr_off[m] = off;
+						a.out[m] = res;
+						int k = 0;
+						while (n > split_class_cap(k)) ++k;
+						const int slot = atomicAdd(&a.cls_cnt[k], 1);
+						a.cls_lists[(size_t)k * a.cls_stride + slot] = m;
+					}
+				}
+				m = -1;
+				continue;
+			}
 			// ---- phase 3: Prim on the mutual-reachability graph -------------------------------------
 			// (prim_segment above: live points in registers, compacted whenever a slot per thread frees up)
 			static_assert(kKeyShift == 13, "prim_segment multiplies by 8192");
-			{
+			if constexpr (MODE == kModeBack) {
+				// done by prim_kernel: nodes in the order they were added, with the weight of the edge that added them
+				const uint32_t *pk = a.scr_pkey + (size_t)a.scr_off[m];
+				if (tid == 0) order[0] = 0;
+				for (int e = tid; e < n - 1; e += NT) {
+					const uint32_t g = pk[e];
+					order[e + 1] = (uint16_t)(g & kKeyIdxMask);
+					wp[e] = g >> kKeyShift;
+				}
+			} else {
 				// storage the sort and the tree use later: pinfo = d4 + rank + pe (8 B/point), live-key lists A = a4
 				// (the core distances move into pinfo first), B = pl + queue
 				uint2 *pinfo = reinterpret_cast<uint2 *>(skey);

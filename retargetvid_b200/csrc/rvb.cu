@@ -16,6 +16,7 @@
 #include "../../include/retargetvid_b200.h"
 #include "iou_kernel.cuh"
 #include "map_kernel.cuh"
+#include "prim_kernel.cuh"
 #include "track_kernels.cuh"
 
 using namespace rvb;
@@ -85,6 +86,8 @@ struct rvb_ctx {
 	int device = 0;
 	int n_sm = 0;
 	cudaStream_t own_stream = nullptr;
+	cudaStream_t side_stream = nullptr;   // monolithic launches (chains) run beside the split pipeline
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_map0 = nullptr, ev_map1 = nullptr, ev_stage = nullptr;
 	bool stage_busy = false;
@@ -93,7 +96,9 @@ struct rvb_ctx {
 	int64_t launches = 0;
 	bool phase_on = false;
 	DevBuf phase;
+	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
+	DevBuf scr_pinfo, scr_val, scr_pkey;
 	PinBuf stage, stage_out;
 };
 
@@ -103,7 +108,7 @@ struct rvb_ctx {
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
 static const int kMaxDynSmem = 227 * 1024 - 1024;  // per-CTA opt-in limit minus the kernel's static shared memory
 
-static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs, int small_bytes) {
+static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs, int small_bytes, bool front = false) {
 	SmemLayout L;
 	memset(&L, 0, sizeof(L));
 	int o = 0;
@@ -117,6 +122,15 @@ static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs, int smal
 	L.u_base = o;
 	L.map = o;
 	int c = o;
+	if (front) {
+		// front half of the split pipeline: only the core distances, the occupancy mask and the fallback queue
+		// share the map's storage
+		L.a4 = c; c += 4 * nmax;
+		L.d4 = L.mask = c; c += align_up(H * ((W + 31) / 32) * 4, 16);
+		L.queue = c; c += 2 * nmax;
+		L.total = align_up(std::max(c, L.map + H * WPS), 128);
+		return L;
+	}
 	L.a4 = c; c += 4 * nmax;
 	L.order = c; c += 2 * nmax;
 	L.wp = c; c += 4 * nmax;
@@ -326,6 +340,9 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	CU(cudaEventCreate(&c->ev_map0));
 	CU(cudaEventCreate(&c->ev_map1));
 	CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+	CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	RingTable t;
 	build_ring_table(t);
 	CU(cudaMemcpyToSymbol(c_rings, &t, sizeof(t)));
@@ -334,6 +351,17 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	CU(cudaFuncSetAttribute(map_kernel<512, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+	CU(cudaFuncSetAttribute(map_kernel<256, 12, kModeFront>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<256, 6, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<256, 8, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 6, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(prim_kernel<1, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+	CU(cudaFuncSetAttribute(prim_kernel<2, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+	CU(cudaFuncSetAttribute(prim_kernel<4, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+	{
+		const char *e = getenv("RVB_NO_SPLIT");
+		c->split = !(e && e[0] == '1');
+	}
 	*out = c;
 	return RVB_OK;
 }
@@ -343,13 +371,16 @@ extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->maps_in, &c->maps_nhw, &c->filt, &c->meta, &c->mapout, &c->series, &c->scratch,
-					  &c->boxes, &c->misc, &c->iou_a, &c->iou_b, &c->iou_c};
+					  &c->boxes, &c->misc, &c->iou_a, &c->iou_b, &c->iou_c, &c->scr_pinfo, &c->scr_val, &c->scr_pkey};
 	for (DevBuf *b : bufs) b->release();
 	c->stage.release();
 	c->stage_out.release();
 	if (c->ev_map0) cudaEventDestroy(c->ev_map0);
 	if (c->ev_map1) cudaEventDestroy(c->ev_map1);
 	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->side_stream) cudaStreamDestroy(c->side_stream);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return RVB_OK;
@@ -412,21 +443,21 @@ extern "C" int rvb_params_default(rvb_params *p, int use_best_settings) {
 }
 
 // one launch of the map kernel family
-template <int NT, int TPT>
-static int launch_map(rvb_ctx *c, MapArgs a, int H, int W, int WPS, int grid) {
-	a.lay = make_layout(NT * TPT, H, WPS, W, a.mcs, a.resize_on ? a.Hs * a.WSs : 0);
+template <int NT, int TPT, int MODE = kModeMono>
+static int launch_map(rvb_ctx *c, MapArgs a, int H, int W, int WPS, int grid, cudaStream_t stream = nullptr) {
+	a.lay = make_layout(NT * TPT, H, WPS, W, a.mcs, a.resize_on ? a.Hs * a.WSs : 0, MODE == kModeFront);
 	if (a.lay.total > (NT * TPT > 4096 ? kMaxDynSmem : 200 * 1024)) return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d needs %d B of shared memory", H, W, a.lay.total);
-	map_kernel<NT, TPT><<<grid, NT, a.lay.total, c->stream>>>(a);
+	map_kernel<NT, TPT, MODE><<<grid, NT, a.lay.total, stream ? stream : c->stream>>>(a);
 	CU(cudaGetLastError());
 	c->launches += 1;
 	c->map_launches += 1;
 	return RVB_OK;
 }
 
-template <int NT, int TPT>
+template <int NT, int TPT, int MODE = kModeMono>
 static int occupancy_grid(rvb_ctx *c, int smem, int n_items) {
 	int per_sm = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_kernel<NT, TPT>, NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_kernel<NT, TPT, MODE>, NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
 	int g = c->n_sm * per_sm;
 	if (n_items >= 0) g = std::min(g, std::max(n_items, 1));
 	return std::max(g, 1);
@@ -563,13 +594,22 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	// work list: every map that does not wait for a predecessor; the starts of cut-adjacent chains come
 	// first so that the longest sequential dependencies begin as early as possible.  A chain is walked
 	// by the CTA that took its first map (chain_next), so there are no waves and no inter-CTA waits.
-	std::vector<int> work;
+	// Split pipeline (front -> prim_kernel -> back) for every map outside a chain; chains, and whatever the
+	// front kernel cannot place, stay with the monolithic kernel.
+	ResizeSetup rzs;
+	if (p->resize_factor != 1.0) build_resize(p->resize_factor, H, W, rzs);
+	const bool split = c->split && p->clust_filt && !rzs.on;
+	std::vector<int> work, work_split;
 	work.reserve(NM);
 	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && chain_next[m]) work.push_back(m);
-	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && !chain_next[m]) work.push_back(m);
-	// counters: per capacity class {head, len} of that class's work list
-	std::vector<int> counters(5 * 2, 0);
+	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && !chain_next[m]) (split ? work_split : work).push_back(m);
+	// counters: [0..9] per monolithic capacity class {head, len} of that class's work list; [10,11] the front
+	// kernel's {head, len}; [12..15] lengths of the split size-class lists; [16..19] / [20..23] their heads in the
+	// Prim and back launches; [24,25] the scratch allocator (64 bit)
+	std::vector<int> counters(26, 0);
 	counters[1] = (int)work.size();
+	counters[11] = (int)work_split.size();
+	const int n_split = (int)work_split.size();
 
 	Staging sg;
 	const size_t o_clips = sg.add(clips.data(), clips.size() * sizeof(ClipDev));
@@ -586,8 +626,6 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_ccoef = sg.add(clip_coef.data(), clip_coef.size() * sizeof(int));
 	const size_t o_coefs = sg.add(coefs.data(), coefs.size() * sizeof(FilterCoef));
 	const size_t o_cnt = sg.add(counters.data(), counters.size() * sizeof(int));
-	ResizeSetup rzs;
-	if (p->resize_factor != 1.0) build_resize(p->resize_factor, H, W, rzs);
 	const size_t o_rz = sg.add(rzs.tab.data(), rzs.tab.size() * sizeof(int16_t));
 	const int small_bytes = rzs.on ? rzs.Hs * rzs.WSs : 0;
 	const size_t o_jumps = sg.add(nullptr, (size_t)NM * sizeof(double));
@@ -596,6 +634,9 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf3 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf4 = sg.add(nullptr, (size_t)NM * sizeof(int));
+	const size_t o_work2 = sg.add(work_split.data(), work_split.size() * sizeof(int));
+	const size_t o_cls = sg.add(nullptr, (size_t)kSplitClasses * n_split * sizeof(int));
+	const size_t o_scroff = sg.add(nullptr, (size_t)(split ? NM : 0) * sizeof(int));
 	const size_t o_borders = sg.add(nullptr, (size_t)nc * 4 * sizeof(int));
 	const size_t o_status = sg.add(nullptr, (size_t)nc * sizeof(int));
 	const size_t o_prof = sg.add(nullptr, (size_t)nc * (H + W) * sizeof(uint32_t));
@@ -721,11 +762,34 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		{
 			const int nw = (int)work.size();
 			int *cnt = d_cnt;
+			if (n_split > 0) {
+				// scratch for the points of the split maps: 2048 per map on average; a map that finds it full goes to a
+				// monolithic launch instead
+				const size_t cap = (size_t)std::min<long long>((long long)n_split * 2048, 0x7fffff00LL);
+				if (c->scr_pinfo.ensure(cap * sizeof(uint2)) || c->scr_val.ensure(cap) || c->scr_pkey.ensure(cap * sizeof(uint32_t))) return RVB_ERR_CUDA;
+				a.cls_lists = (int *)(M + o_cls); a.cls_cnt = cnt + 12; a.cls_stride = n_split;
+				a.scr_off = (int *)(M + o_scroff); a.scr_top = (unsigned long long *)(cnt + 24); a.scr_cap = (unsigned int)cap;
+				a.scr_pinfo = (uint2 *)c->scr_pinfo.p; a.scr_val = (uint8_t *)c->scr_val.p; a.scr_pkey = (uint32_t *)c->scr_pkey.p;
+				// the front kernel's overflow (more than 3072 points, or scratch full) lands in the list of the
+				// monolithic class of 4096 points
+				a.list = (const int *)(M + o_work2); a.head = cnt + 10; a.list_len = cnt + 11;
+				a.ovf_list = (int *)(M + o_ovf3); a.ovf_len = cnt + 2 * 3 + 1;
+				int rc = launch_map<256, 12, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 12, kModeFront>(c, make_layout(3072, H, WPS, W, p->hdbscan_min, 0, true).total, n_split));
+				if (rc) return rc;
+			}
 			// capacity classes 1536 / 2048 / 3072 / 4096 / 8192 salient pixels (shared memory per CTA grows with
 			// the capacity, so smaller classes keep more maps in flight per SM): a map that does not fit is
 			// appended to the next class's list by the kernel itself (no host round trip)
 			int *ovf[4] = {(int *)(M + o_ovf1), (int *)(M + o_ovf2), (int *)(M + o_ovf3), (int *)(M + o_ovf4)};
 			const int mcs = p->hdbscan_min;
+			// with the split pipeline the monolithic launches (chains: long sequential dependencies, few maps) go to a
+			// side stream and overlap the Prim / back launches of the same call
+			cudaStream_t mono_st = st;
+			if (n_split > 0) {
+				mono_st = c->side_stream;
+				CU(cudaEventRecord(c->ev_fork, st));
+				CU(cudaStreamWaitEvent(mono_st, c->ev_fork, 0));
+			}
 			for (int k = 0; k < 5; ++k) {
 				a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
 				a.head = cnt + 2 * k;
@@ -734,12 +798,45 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				a.ovf_list = (k < 4) ? ovf[k] : nullptr;
 				a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
 				int rc = RVB_OK;
-				if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nw));
-				if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nw));
-				if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nw));
-				if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nw));
-				if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nw));
+				const int nwk = (k == 0) ? nw : nw + n_split;   // later classes also receive the front kernel's overflow
+				if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
+				if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
+				if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
+				if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
+				if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
 				if (rc) return rc;
+			}
+			if (n_split > 0) {
+				// Prim, one launch per size class: (warps per map, register slots per thread)
+				PrimArgs pa;
+				memset(&pa, 0, sizeof(pa));
+				pa.out = (const MapOut *)c->mapout.p; pa.scr_off = a.scr_off; pa.scr_pinfo = a.scr_pinfo; pa.scr_pkey = a.scr_pkey;
+				pa.phase_cycles = a.phase_cycles;
+				for (int k = 0; k < kSplitClasses; ++k) {
+					pa.list = a.cls_lists + (size_t)k * n_split; pa.list_len = cnt + 12 + k; pa.head = cnt + 16 + k;
+					pa.cap = split_class_cap(k);
+					const int smem = 12 * pa.cap;
+					// 24 slots x 4 registers per thread leave room for 16 warps per SM: a warp issues at most every third
+					// cycle in this loop (half-rate integer pipe + dependent latency), so fewer warps leave issue slots empty
+					if (k == 0) prim_kernel<1, 24><<<std::min(n_split, c->n_sm * 16), 32, smem, st>>>(pa);
+					if (k == 1) prim_kernel<2, 24><<<std::min(n_split, c->n_sm * 8), 64, smem, st>>>(pa);
+					if (k >= 2) prim_kernel<4, 24><<<std::min(n_split, c->n_sm * 4), 128, smem, st>>>(pa);
+					CU(cudaGetLastError());
+					c->launches += 1;
+					c->map_launches += 1;
+				}
+				// back half: sort .. results, with the capacity classes of the monolithic kernel
+				a.ovf_list = nullptr; a.ovf_len = nullptr;
+				for (int k = 0; k < kSplitClasses; ++k) {
+					a.list = a.cls_lists + (size_t)k * n_split; a.list_len = cnt + 12 + k; a.head = cnt + 20 + k;
+					int rc = RVB_OK;
+					if (k <= 1) rc = launch_map<256, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 6, kModeBack>(c, make_layout(1536, H, WPS, W, mcs, 0).total, n_split));
+					if (k == 2) rc = launch_map<256, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 8, kModeBack>(c, make_layout(2048, H, WPS, W, mcs, 0).total, n_split));
+					if (k == 3) rc = launch_map<512, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 6, kModeBack>(c, make_layout(3072, H, WPS, W, mcs, 0).total, n_split));
+					if (rc) return rc;
+				}
+				CU(cudaEventRecord(c->ev_join, mono_st));
+				CU(cudaStreamWaitEvent(st, c->ev_join, 0));
 			}
 		}
 	}
