@@ -128,12 +128,14 @@ struct MapArgs {
 	uint2 *scr_pinfo;          // {core distance, (y << 8) | x}
 	uint8_t *scr_val;          // pixel values
 	uint32_t *scr_pkey;        // Prim output: (edge weight << 13) | node, in the order the nodes were added
+	int force_class;           // front: >= 0 puts every map into this size class (chain sets: few maps, latency matters)
+	uint8_t *skip;             // front: 1 = an earlier map of this chain went to a monolithic launch, which walks the rest
 	SmemLayout lay;
 };
 
 // split pipeline: point-count classes of the Prim / back launches
-constexpr int kSplitClasses = 4;
-__host__ __device__ constexpr int split_class_cap(int k) { return k == 0 ? 768 : k == 1 ? 1536 : k == 2 ? 2048 : 3072; }
+constexpr int kSplitClasses = 5;
+__host__ __device__ constexpr int split_class_cap(int k) { return k == 0 ? 768 : k == 1 ? 1536 : k == 2 ? 2048 : k == 3 ? 3072 : 4096; }
 constexpr int kModeMono = 0, kModeFront = 1, kModeBack = 2;
 
 __constant__ RingTable c_rings;
@@ -595,6 +597,7 @@ struct MapScalars {
 	int maxcl;
 	int n_clusters;
 	int fb_count;
+	int scr_slot;   // front: this map's offset in the scratch arrays, or -1
 	int err;
 	uint32_t rootminw;
 	uint32_t root_edge;
@@ -870,7 +873,8 @@ __global__ void __launch_bounds__(256) map_stream_kernel(const uint8_t *__restri
 // resident CTAs per SM the register budget must allow, per capacity class (shared memory bounds the same)
 template <int NT, int TPT, int MODE>
 struct MapKernelCfg {
-	static constexpr int kMinBlocks = (MODE == kModeFront) ? 4 : (NT * TPT <= 1536) ? 5 : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1;
+	// (the monolithic kernel keeps Prim's point registers and the tree code's temporaries alive together: 64 registers)
+	static constexpr int kMinBlocks = (MODE == kModeFront) ? 4 : (NT * TPT <= 1536) ? (MODE == kModeMono ? 4 : 5) : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1;
 };
 
 // MODE kModeMono: the whole path for one map after the other (cut-adjacent chains, the largest classes, resize).
@@ -912,6 +916,9 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 			__syncthreads();
 			m = S.map_idx;
 			if (m < 0) break;
+			if constexpr (MODE == kModeFront) {
+				if (a.skip != nullptr && a.skip[m]) { m = -1; continue; }
+			}
 		}
 		long long phase_t0 = clock64();
 		MapOut res;
@@ -1078,6 +1085,10 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 				if (a.ovf_list != nullptr) {
 					const int k = atomicAdd(a.ovf_len, 1);
 					a.ovf_list[k] = m;
+					if constexpr (MODE == kModeFront) {
+						// the monolithic launch walks the rest of this chain: later front launches leave it alone
+						if (a.skip != nullptr) for (int q = m; a.chain_next[q]; ++q) a.skip[q + 1] = 1;
+					}
 				} else {
 					res.flags = kFlagOverflow;
 					a.out[m] = res;
@@ -1200,15 +1211,16 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 				if (tid == 0) {
 					const unsigned long long need = (unsigned long long)((n + 15) & ~15);
 					const unsigned long long off = atomicAdd(a.scr_top, need);
-					S.fb_count = (off + need <= (unsigned long long)a.scr_cap) ? (int)off : -1;
+					S.scr_slot = (off + need <= (unsigned long long)a.scr_cap) ? (int)off : -1;
 				}
 				__syncthreads();
-				const int off = S.fb_count;
+				const int off = S.scr_slot;
 				if (off < 0) {
 					// scratch exhausted: a monolithic launch takes the map
 					if (tid == 0) {
 						const int k = atomicAdd(a.ovf_len, 1);
 						a.ovf_list[k] = m;
+						if (a.skip != nullptr) for (int q = m; a.chain_next[q]; ++q) a.skip[q + 1] = 1;
 					}
 				} else {
 					for (int j = tid; j < n; j += NT) {
@@ -1220,6 +1232,7 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 						a.out[m] = res;
 						int k = 0;
 						while (n > split_class_cap(k)) ++k;
+						if (a.force_class >= 0) k = a.force_class;
 						const int slot = atomicAdd(&a.cls_cnt[k], 1);
 						a.cls_lists[(size_t)k * a.cls_stride + slot] = m;
 					}
@@ -1334,54 +1347,119 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 			RVB_PHASE(5);  // Cartesian tree
 			// ---- phase 4c: condensed tree over the big nodes, breadth first (_condense_tree) ---------
 			// rank[] is dead from here: its storage becomes relabel[]
+			//
+			// The library walks the dendrogram node by node; almost all of that walk runs down "spines" (a node with
+			// one child of at least min_cluster_size points passes its label on), which only a true split or a dead end
+			// terminates.  Here the spines are contracted in parallel (pointer jumping towards the spine's head), one
+			// thread replays the breadth-first order over whole spines -- labels are numbered in the order the library
+			// dequeues the splits: by depth, then by queue position -- and the labels are spread back in parallel.
 			const int mcs = a.mcs;
-			if (tid == 0) {
-				S.err = 0;
-				S.rootminw = 0xFFFFFFFFu;
-				int ncl = 1;
-				cl_stab[0] = 0ull; cl_birth[0] = 0ull; cl_parent[0] = kNone16; cl_ch0[0] = kNone16; cl_ch1[0] = kNone16;
-				int qh = 0, qt = 0;
-				const int root = (int)S.root_edge;
-				relabel[root] = 0;
-				queue[qt++] = (uint16_t)root;
-				uint32_t rootminw = 0xFFFFFFFFu;
-				while (qh < qt) {
-					const int e = queue[qh++];
-					const int c = relabel[e];
-					const int lc = e + 1 - (int)Lp1[e];
-					const int rc = (int)Rr[e] - e;
-					if (lc >= mcs && rc >= mcs) {
-						if (ncl + 2 > L.ncmax) { S.err = 1; break; }
-						const uint32_t w = wp[e];
-						const unsigned long long lam = lambda_fix(w);
-						const int ca = ncl++, cb = ncl++;
-						cl_stab[ca] = 0ull; cl_stab[cb] = 0ull;
-						cl_birth[ca] = lam; cl_birth[cb] = lam;
-						cl_parent[ca] = (uint16_t)c; cl_parent[cb] = (uint16_t)c;
-						cl_ch0[ca] = kNone16; cl_ch1[ca] = kNone16; cl_ch0[cb] = kNone16; cl_ch1[cb] = kNone16;
-						cl_ch0[c] = (uint16_t)ca; cl_ch1[c] = (uint16_t)cb;
-						cl_stab[c] += (lam - cl_birth[c]) * (unsigned long long)(lc + rc);
-						if (c == 0) rootminw = min(rootminw, w);
-						relabel[cL[e]] = (uint16_t)ca;
-						relabel[cR[e]] = (uint16_t)cb;
-						queue[qt++] = cL[e];
-						queue[qt++] = cR[e];
-					} else if (lc >= mcs) {
-						relabel[cL[e]] = (uint16_t)c;
-						queue[qt++] = cL[e];
-					} else if (rc >= mcs) {
-						relabel[cR[e]] = (uint16_t)c;
-						queue[qt++] = cR[e];
+			{
+				uint16_t *up = queue;       // parent along the spine, after the jumping the spine's head, finally its label
+				uint16_t *dist = relabel;   // hops from the head; for a head: index of its spine record
+				uint16_t *sp_tail = cl_label, *sp_end = cl_selanc;   // per spine: last node, depth of that node
+				uint16_t *sp_lnk = reinterpret_cast<uint16_t *>(cl_acc), *sp_lab = sp_lnk + L.ncmax;
+				uint16_t *sp_head = sp_lnk;   // (until the replay starts)
+				auto left_size = [&](int e) { return e + 1 - (int)Lp1[e]; };
+				auto right_size = [&](int e) { return (int)Rr[e] - e; };
+				if (tid == 0) { S.err = 0; S.sort_cnt[0] = 0; }
+				for (int e = tid; e < ne; e += NT) {
+					const uint16_t p = pe[e];
+					bool follow = false;
+					if (p != kNone16 && left_size(e) + right_size(e) >= mcs) follow = !(left_size(p) >= mcs && right_size(p) >= mcs);
+					up[e] = follow ? p : (uint16_t)e;
+					dist[e] = follow ? 1 : 0;
+				}
+				__syncthreads();
+				for (int span = 1; span < ne; span <<= 1) {
+					uint16_t nu[TPT], nd[TPT];
+#pragma unroll
+					for (int i = 0; i < TPT; ++i) {
+						const int e = tid + i * NT;
+						if (e < ne) {
+							const int u = up[e];
+							nu[i] = up[u];
+							nd[i] = (uint16_t)(dist[e] + dist[u]);
+						}
+					}
+					__syncthreads();
+#pragma unroll
+					for (int i = 0; i < TPT; ++i) {
+						const int e = tid + i * NT;
+						if (e < ne) { up[e] = nu[i]; dist[e] = nd[i]; }
+					}
+					__syncthreads();
+				}
+				// one record per spine, written by its last node
+				for (int e = tid; e < ne; e += NT) {
+					const int lc = left_size(e), rc = right_size(e);
+					if (lc + rc >= mcs && ((lc >= mcs) == (rc >= mcs))) {
+						const int r = atomicAdd(&S.sort_cnt[0], 1);
+						if (r < L.ncmax) { sp_head[r] = up[e]; sp_tail[r] = (uint16_t)e; sp_end[r] = dist[e]; }
 					}
 				}
-				S.ncl = ncl;
-				S.rootminw = rootminw;
-			}
-			__syncthreads();
-			if (S.err) {
-				if (tid == 0) { res.flags |= kFlagClusterCapacity; a.out[m] = res; }
-				m = -1;
-				continue;
+				__syncthreads();
+				const int nrec = S.sort_cnt[0];   // = number of condensed-tree clusters
+				if (nrec > L.ncmax) {
+					if (tid == 0) { res.flags |= kFlagClusterCapacity; a.out[m] = res; }
+					m = -1;
+					continue;
+				}
+				for (int r = tid; r < nrec; r += NT) dist[sp_head[r]] = (uint16_t)r;
+				__syncthreads();
+				if (tid == 0) {
+					int ncl = 1;
+					cl_stab[0] = 0ull; cl_birth[0] = 0ull; cl_parent[0] = kNone16; cl_ch0[0] = kNone16; cl_ch1[0] = kNone16;
+					uint32_t rootminw = 0xFFFFFFFFu;
+					int first = dist[S.root_edge];
+					sp_lab[first] = 0;
+					sp_lnk[first] = kNone16;
+					while (first != kNone16) {
+						// the nodes the library dequeues next are the spine ends of the smallest depth, in list order
+						int dmin = 0x7fffffff;
+						for (int r = first; r != kNone16; r = sp_lnk[r]) dmin = min(dmin, (int)sp_end[r]);
+						int prev = kNone16;
+						for (int r = first; r != kNone16;) {
+							const int nxt = sp_lnk[r];
+							if ((int)sp_end[r] != dmin) { prev = r; r = nxt; continue; }
+							const int e = sp_tail[r];
+							const int c = sp_lab[r];
+							const int lc = left_size(e), rc = right_size(e);
+							if (lc >= mcs && rc >= mcs) {
+								const uint32_t w = wp[e];
+								const unsigned long long lam = lambda_fix(w);
+								const int ca = ncl++, cb = ncl++;
+								cl_stab[ca] = 0ull; cl_stab[cb] = 0ull;
+								cl_birth[ca] = lam; cl_birth[cb] = lam;
+								cl_parent[ca] = (uint16_t)c; cl_parent[cb] = (uint16_t)c;
+								cl_ch0[ca] = kNone16; cl_ch1[ca] = kNone16; cl_ch0[cb] = kNone16; cl_ch1[cb] = kNone16;
+								cl_ch0[c] = (uint16_t)ca; cl_ch1[c] = (uint16_t)cb;
+								cl_stab[c] += (lam - cl_birth[c]) * (unsigned long long)(lc + rc);
+								if (c == 0) rootminw = min(rootminw, w);
+								// the two children start spines one level down; they take this spine's place in the order
+								const int rl = dist[cL[e]], rr = dist[cR[e]];
+								sp_lab[rl] = (uint16_t)ca; sp_lab[rr] = (uint16_t)cb;
+								sp_end[rl] = (uint16_t)(sp_end[rl] + dmin + 1); sp_end[rr] = (uint16_t)(sp_end[rr] + dmin + 1);
+								sp_lnk[rl] = (uint16_t)rr; sp_lnk[rr] = (uint16_t)nxt;
+								if (prev == kNone16) first = rl; else sp_lnk[prev] = (uint16_t)rl;
+								prev = rr;
+							} else {
+								if (prev == kNone16) first = nxt; else sp_lnk[prev] = (uint16_t)nxt;
+							}
+							r = nxt;
+						}
+					}
+					S.ncl = ncl;
+					S.rootminw = rootminw;
+				}
+				__syncthreads();
+				// every big node takes the label of its spine (up[e] is read by the thread that owns e only)
+				for (int e = tid; e < ne; e += NT)
+					if (left_size(e) + right_size(e) >= mcs) up[e] = sp_lab[dist[up[e]]];
+				__syncthreads();
+				for (int e = tid; e < ne; e += NT)
+					if (left_size(e) + right_size(e) >= mcs) relabel[e] = up[e];
+				__syncthreads();
 			}
 
 			RVB_PHASE(6);  // condensed-tree BFS
@@ -1617,7 +1695,8 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 		if (tid == 0) a.out[m] = res;
 		RVB_PHASE(10);  // results
 		// the filtered map just stored is the blend source of map m+1 (smartVidCrop.py:2369-2373)
-		m = (a.chain_next != nullptr && a.chain_next[m]) ? (m + 1) : -1;
+		// (only the monolithic kernel walks a chain; the split pipeline runs chains one depth per launch)
+		m = (MODE == kModeMono && a.chain_next != nullptr && a.chain_next[m]) ? (m + 1) : -1;
 	}
 }
 

@@ -96,6 +96,8 @@ struct rvb_ctx {
 	int64_t launches = 0;
 	bool phase_on = false;
 	DevBuf phase;
+	bool chain_levels = false;  // RVB_CHAIN_LEVELS=1: chains go through the split pipeline one depth per launch; default: the
+	                            // monolithic kernel walks them on the side stream (measured 6 % faster at 3 batches in flight)
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
 	DevBuf scr_pinfo, scr_val, scr_pkey;
@@ -340,7 +342,17 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	CU(cudaEventCreate(&c->ev_map0));
 	CU(cudaEventCreate(&c->ev_map1));
 	CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
-	CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+	{
+		// experiment knobs (profiling only): RVB_SIDE_PRIO = CUDA priority of the side stream, RVB_CHAIN_LEVELS=1
+		const char *e = getenv("RVB_SIDE_PRIO");
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		int prio = e ? atoi(e) : 0;
+		prio = std::max(hi, std::min(lo, prio));
+		CU(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio));
+		e = getenv("RVB_CHAIN_LEVELS");
+		c->chain_levels = (e && e[0] == '1');
+	}
 	CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	RingTable t;
@@ -351,7 +363,9 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	CU(cudaFuncSetAttribute(map_kernel<512, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-	CU(cudaFuncSetAttribute(map_kernel<256, 12, kModeFront>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<256, 16, kModeFront>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 8, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(prim_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 6, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 8, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 6, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -591,25 +605,54 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		clip_coef[i] = ci;
 	}
 	if (scratch_doubles > 0x7fffffffLL) return fail(RVB_ERR_INVALID, "batch too large (scratch)");
-	// work list: every map that does not wait for a predecessor; the starts of cut-adjacent chains come
-	// first so that the longest sequential dependencies begin as early as possible.  A chain is walked
-	// by the CTA that took its first map (chain_next), so there are no waves and no inter-CTA waits.
-	// Split pipeline (front -> prim_kernel -> back) for every map outside a chain; chains, and whatever the
-	// front kernel cannot place, stay with the monolithic kernel.
+	// Monolithic path: every map that does not wait for a predecessor is a work item; a chain is walked by the CTA that
+	// took its first map (chain_next), so there are no waves and no inter-CTA waits.
+	// Split pipeline (front -> prim_kernel -> back), the default: see the work sets below.
 	ResizeSetup rzs;
 	if (p->resize_factor != 1.0) build_resize(p->resize_factor, H, W, rzs);
 	const bool split = c->split && p->clust_filt && !rzs.on;
-	std::vector<int> work, work_split;
+	// Work sets of the split pipeline: set 0 = every map outside a chain; set 1 + L = the chain maps at depth L
+	// (depth 0 = chain heads).  A set runs front -> Prim -> back; set 1 + L needs the filtered maps of set L.
+	constexpr int kMaxChainDepth = 8;
+	std::vector<int> depth(NM, 0);
+	int max_depth = 0;
+	for (int m = 0; m < NM; ++m) {
+		depth[m] = (pred[m] < 0) ? 0 : depth[m - 1] + 1;   // the predecessor of map m is map m - 1
+		max_depth = std::max(max_depth, depth[m]);
+	}
+	const bool split_chains = split && max_depth < kMaxChainDepth && c->chain_levels;
+	std::vector<int> work;                    // monolithic launches: chain heads (the CTA walks the chain)
+	std::vector<std::vector<int>> sets;       // split pipeline
+	if (split) sets.resize(split_chains ? 2 + max_depth : 1);
 	work.reserve(NM);
-	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && chain_next[m]) work.push_back(m);
-	for (int m = 0; m < NM; ++m) if (pred[m] < 0 && !chain_next[m]) (split ? work_split : work).push_back(m);
-	// counters: [0..9] per monolithic capacity class {head, len} of that class's work list; [10,11] the front
-	// kernel's {head, len}; [12..15] lengths of the split size-class lists; [16..19] / [20..23] their heads in the
-	// Prim and back launches; [24,25] the scratch allocator (64 bit)
-	std::vector<int> counters(26, 0);
+	for (int m = 0; m < NM; ++m) {
+		const bool in_chain = pred[m] >= 0 || chain_next[m];
+		if (!split) { if (pred[m] < 0) work.push_back(m); }
+		else if (!in_chain) sets[0].push_back(m);
+		else if (split_chains) sets[1 + depth[m]].push_back(m);
+		else if (pred[m] < 0) work.push_back(m);
+	}
+	if (!split) {
+		// chain heads first: the longest sequential dependencies start as early as possible
+		std::stable_partition(work.begin(), work.end(), [&](int m) { return chain_next[m] != 0; });
+	}
+	const int n_sets = (int)sets.size();
+	// counters: [0..9] per monolithic capacity class {head, len} of that class's work list; then per split set
+	// kSetCounters ints: {front head, front len, class lengths[5], Prim heads[5], back heads[5]}; then the scratch
+	// allocator (64 bit)
+	constexpr int kSetCounters = 2 + 3 * kSplitClasses + 1;
+	const int cnt_scr = (10 + n_sets * kSetCounters + 1) & ~1;
+	std::vector<int> counters(cnt_scr + 2, 0);
 	counters[1] = (int)work.size();
-	counters[11] = (int)work_split.size();
-	const int n_split = (int)work_split.size();
+	std::vector<int> set_list_off(n_sets, 0);   // offsets (ints) into the concatenated front lists
+	std::vector<int> split_all;
+	int n_split = 0;
+	for (int k = 0; k < n_sets; ++k) {
+		counters[10 + k * kSetCounters + 1] = (int)sets[k].size();
+		set_list_off[k] = n_split;
+		n_split += (int)sets[k].size();
+		split_all.insert(split_all.end(), sets[k].begin(), sets[k].end());
+	}
 
 	Staging sg;
 	const size_t o_clips = sg.add(clips.data(), clips.size() * sizeof(ClipDev));
@@ -634,9 +677,10 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf3 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf4 = sg.add(nullptr, (size_t)NM * sizeof(int));
-	const size_t o_work2 = sg.add(work_split.data(), work_split.size() * sizeof(int));
+	const size_t o_work2 = sg.add(split_all.data(), split_all.size() * sizeof(int));
 	const size_t o_cls = sg.add(nullptr, (size_t)kSplitClasses * n_split * sizeof(int));
 	const size_t o_scroff = sg.add(nullptr, (size_t)(split ? NM : 0) * sizeof(int));
+	const size_t o_skip = sg.add(nullptr, (size_t)(split ? NM : 0));
 	const size_t o_borders = sg.add(nullptr, (size_t)nc * 4 * sizeof(int));
 	const size_t o_status = sg.add(nullptr, (size_t)nc * sizeof(int));
 	const size_t o_prof = sg.add(nullptr, (size_t)nc * (H + W) * sizeof(uint32_t));
@@ -730,6 +774,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	if (n_slots > 0 && c->filt.ensure((size_t)n_slots * H * WPS)) return RVB_ERR_CUDA;
 	MapArgs a;
 	memset(&a, 0, sizeof(a));
+	a.force_class = -1;
 	a.maps_u8 = d_u8; a.maps_f32 = d_f32; a.H = H; a.W = W; a.WPS = WPS; a.gstride = gstride;
 	a.pred = (const int *)(M + o_pred); a.store = (const int *)(M + o_store); a.map_clip = (const int *)(M + o_mclip);
 	a.chain_next = (const uint8_t *)(M + o_chain);
@@ -762,80 +807,105 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		{
 			const int nw = (int)work.size();
 			int *cnt = d_cnt;
-			if (n_split > 0) {
-				// scratch for the points of the split maps: 2048 per map on average; a map that finds it full goes to a
-				// monolithic launch instead
-				const size_t cap = (size_t)std::min<long long>((long long)n_split * 2048, 0x7fffff00LL);
-				if (c->scr_pinfo.ensure(cap * sizeof(uint2)) || c->scr_val.ensure(cap) || c->scr_pkey.ensure(cap * sizeof(uint32_t))) return RVB_ERR_CUDA;
-				a.cls_lists = (int *)(M + o_cls); a.cls_cnt = cnt + 12; a.cls_stride = n_split;
-				a.scr_off = (int *)(M + o_scroff); a.scr_top = (unsigned long long *)(cnt + 24); a.scr_cap = (unsigned int)cap;
-				a.scr_pinfo = (uint2 *)c->scr_pinfo.p; a.scr_val = (uint8_t *)c->scr_val.p; a.scr_pkey = (uint32_t *)c->scr_pkey.p;
-				// the front kernel's overflow (more than 3072 points, or scratch full) lands in the list of the
-				// monolithic class of 4096 points
-				a.list = (const int *)(M + o_work2); a.head = cnt + 10; a.list_len = cnt + 11;
-				a.ovf_list = (int *)(M + o_ovf3); a.ovf_len = cnt + 2 * 3 + 1;
-				int rc = launch_map<256, 12, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 12, kModeFront>(c, make_layout(3072, H, WPS, W, p->hdbscan_min, 0, true).total, n_split));
-				if (rc) return rc;
-			}
-			// capacity classes 1536 / 2048 / 3072 / 4096 / 8192 salient pixels (shared memory per CTA grows with
-			// the capacity, so smaller classes keep more maps in flight per SM): a map that does not fit is
-			// appended to the next class's list by the kernel itself (no host round trip)
 			int *ovf[4] = {(int *)(M + o_ovf1), (int *)(M + o_ovf2), (int *)(M + o_ovf3), (int *)(M + o_ovf4)};
 			const int mcs = p->hdbscan_min;
-			// with the split pipeline the monolithic launches (chains: long sequential dependencies, few maps) go to a
-			// side stream and overlap the Prim / back launches of the same call
-			cudaStream_t mono_st = st;
-			if (n_split > 0) {
-				mono_st = c->side_stream;
-				CU(cudaEventRecord(c->ev_fork, st));
-				CU(cudaStreamWaitEvent(mono_st, c->ev_fork, 0));
-			}
-			for (int k = 0; k < 5; ++k) {
-				a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
-				a.head = cnt + 2 * k;
-				a.list_len = cnt + 2 * k + 1;
-				// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
-				a.ovf_list = (k < 4) ? ovf[k] : nullptr;
-				a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
-				int rc = RVB_OK;
-				const int nwk = (k == 0) ? nw : nw + n_split;   // later classes also receive the front kernel's overflow
-				if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
-				if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
-				if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
-				if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
-				if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nwk), mono_st);
+			// capacity classes 1536 / 2048 / 3072 / 4096 / 8192 salient pixels of the monolithic kernel (shared memory
+			// per CTA grows with the capacity, so smaller classes keep more maps in flight per SM): a map that does not
+			// fit is appended to the next class's list by the kernel itself (no host round trip)
+			auto launch_mono = [&](int k_first, cudaStream_t stream) -> int {
+				for (int k = k_first; k < 5; ++k) {
+					a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
+					a.head = cnt + 2 * k;
+					a.list_len = cnt + 2 * k + 1;
+					// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
+					a.ovf_list = (k < 4) ? ovf[k] : nullptr;
+					a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
+					int rc = RVB_OK;
+					const int nwk = (k == 0) ? nw : nw + n_split;   // later classes also receive overflow
+					if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nwk), stream);
+					if (k == 1) rc = launch_map<256, 8>(c, a, H, W, WPS, occupancy_grid<256, 8>(c, make_layout(2048, H, WPS, W, mcs, small_bytes).total, nwk), stream);
+					if (k == 2) rc = launch_map<512, 6>(c, a, H, W, WPS, occupancy_grid<512, 6>(c, make_layout(3072, H, WPS, W, mcs, small_bytes).total, nwk), stream);
+					if (k == 3) rc = launch_map<512, 8>(c, a, H, W, WPS, occupancy_grid<512, 8>(c, make_layout(4096, H, WPS, W, mcs, small_bytes).total, nwk), stream);
+					if (k == 4) rc = launch_map<512, 16>(c, a, H, W, WPS, occupancy_grid<512, 16>(c, make_layout(8192, H, WPS, W, mcs, small_bytes).total, nwk), stream);
+					if (rc) return rc;
+				}
+				return RVB_OK;
+			};
+			if (!split) {
+				int rc = launch_mono(0, st);
 				if (rc) return rc;
-			}
-			if (n_split > 0) {
-				// Prim, one launch per size class: (warps per map, register slots per thread)
+			} else {
+				// scratch for the points of the split maps: 2048 per map on average; a map that finds it full goes to a
+				// monolithic launch instead
+				const size_t cap = (size_t)std::min<long long>((long long)n_split * 2048 + 8192, 0x7fffff00LL);
+				if (c->scr_pinfo.ensure(cap * sizeof(uint2)) || c->scr_val.ensure(cap) || c->scr_pkey.ensure(cap * sizeof(uint32_t))) return RVB_ERR_CUDA;
+				a.scr_off = (int *)(M + o_scroff); a.scr_top = (unsigned long long *)(cnt + cnt_scr); a.scr_cap = (unsigned int)cap;
+				a.scr_pinfo = (uint2 *)c->scr_pinfo.p; a.scr_val = (uint8_t *)c->scr_val.p; a.scr_pkey = (uint32_t *)c->scr_pkey.p;
+				a.skip = M + o_skip;
 				PrimArgs pa;
 				memset(&pa, 0, sizeof(pa));
 				pa.out = (const MapOut *)c->mapout.p; pa.scr_off = a.scr_off; pa.scr_pinfo = a.scr_pinfo; pa.scr_pkey = a.scr_pkey;
 				pa.phase_cycles = a.phase_cycles;
-				for (int k = 0; k < kSplitClasses; ++k) {
-					pa.list = a.cls_lists + (size_t)k * n_split; pa.list_len = cnt + 12 + k; pa.head = cnt + 16 + k;
-					pa.cap = split_class_cap(k);
-					const int smem = 12 * pa.cap;
-					// 24 slots x 4 registers per thread leave room for 16 warps per SM: a warp issues at most every third
-					// cycle in this loop (half-rate integer pipe + dependent latency), so fewer warps leave issue slots empty
-					if (k == 0) prim_kernel<1, 24><<<std::min(n_split, c->n_sm * 16), 32, smem, st>>>(pa);
-					if (k == 1) prim_kernel<2, 24><<<std::min(n_split, c->n_sm * 8), 64, smem, st>>>(pa);
-					if (k >= 2) prim_kernel<4, 24><<<std::min(n_split, c->n_sm * 4), 128, smem, st>>>(pa);
-					CU(cudaGetLastError());
-					c->launches += 1;
-					c->map_launches += 1;
+				// front: load .. core distances.  Its overflow (more than 4096 points, or scratch full) lands in the list
+				// of the monolithic class of 8192 points, which also walks the rest of that map's chain.
+				auto launch_front = [&](int set, cudaStream_t stream) -> int {
+					const int ns = (int)sets[set].size();
+					if (ns == 0) return RVB_OK;
+					int *sc = cnt + 10 + set * kSetCounters;
+					a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
+					a.cls_lists = (int *)(M + o_cls) + (size_t)kSplitClasses * set_list_off[set]; a.cls_cnt = sc + 2; a.cls_stride = ns;
+					a.ovf_list = ovf[3]; a.ovf_len = cnt + 2 * 4 + 1;
+					// a chain set has few maps and the next depth waits for it: one launch with the widest shape per stage
+					a.force_class = (set > 0) ? kSplitClasses - 1 : -1;
+					return launch_map<256, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 16, kModeFront>(c, make_layout(4096, H, WPS, W, mcs, 0, true).total, ns), stream);
+				};
+				// Prim and back, one launch each per size class
+				auto launch_prim_back = [&](int set, cudaStream_t stream) -> int {
+					const int ns = (int)sets[set].size();
+					if (ns == 0) return RVB_OK;
+					int *sc = cnt + 10 + set * kSetCounters;
+					int *lists = (int *)(M + o_cls) + (size_t)kSplitClasses * set_list_off[set];
+					const int k_first = (set > 0) ? kSplitClasses - 1 : 0;
+					for (int k = k_first; k < kSplitClasses; ++k) {
+						pa.list = lists + (size_t)k * ns; pa.list_len = sc + 2 + k; pa.head = sc + 2 + kSplitClasses + k;
+						pa.cap = split_class_cap(k);
+						const int smem = 12 * pa.cap;
+						// (warps per map, register slots per thread): 16 warps per SM in every class -- a warp issues at most
+						// every third cycle in this loop (half-rate integer pipe + dependent latency)
+						if (k == 0) prim_kernel<1, 24><<<std::min(ns, c->n_sm * 16), 32, smem, stream>>>(pa);
+						if (k == 1) prim_kernel<2, 24><<<std::min(ns, c->n_sm * 8), 64, smem, stream>>>(pa);
+						if (k == 2 || k == 3) prim_kernel<4, 24><<<std::min(ns, c->n_sm * 4), 128, smem, stream>>>(pa);
+						if (k == 4) prim_kernel<8, 16><<<std::min(ns, c->n_sm * 2), 256, smem, stream>>>(pa);
+						CU(cudaGetLastError());
+						c->launches += 1;
+						c->map_launches += 1;
+					}
+					a.ovf_list = nullptr; a.ovf_len = nullptr;
+					for (int k = k_first; k < kSplitClasses; ++k) {
+						a.list = lists + (size_t)k * ns; a.list_len = sc + 2 + k; a.head = sc + 2 + 2 * kSplitClasses + k;
+						int rc = RVB_OK;
+						if (k <= 1) rc = launch_map<256, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 6, kModeBack>(c, make_layout(1536, H, WPS, W, mcs, 0).total, ns), stream);
+						if (k == 2) rc = launch_map<256, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 8, kModeBack>(c, make_layout(2048, H, WPS, W, mcs, 0).total, ns), stream);
+						if (k == 3) rc = launch_map<512, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 6, kModeBack>(c, make_layout(3072, H, WPS, W, mcs, 0).total, ns), stream);
+						if (k == 4) rc = launch_map<512, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 8, kModeBack>(c, make_layout(4096, H, WPS, W, mcs, 0).total, ns), stream);
+						if (rc) return rc;
+					}
+					return RVB_OK;
+				};
+				// main stream: the maps outside chains.  Side stream: the chains, one depth after the other (few maps,
+				// long dependencies), then whatever overflowed into the monolithic kernel.
+				int rc = launch_front(0, st);
+				if (rc) return rc;
+				cudaStream_t side = getenv("RVB_NO_SIDE") ? st : c->side_stream;
+				CU(cudaEventRecord(c->ev_fork, st));
+				CU(cudaStreamWaitEvent(side, c->ev_fork, 0));
+				if ((rc = launch_prim_back(0, st))) return rc;
+				for (int k = 1; k < n_sets; ++k) {
+					if ((rc = launch_front(k, side))) return rc;
+					if ((rc = launch_prim_back(k, side))) return rc;
 				}
-				// back half: sort .. results, with the capacity classes of the monolithic kernel
-				a.ovf_list = nullptr; a.ovf_len = nullptr;
-				for (int k = 0; k < kSplitClasses; ++k) {
-					a.list = a.cls_lists + (size_t)k * n_split; a.list_len = cnt + 12 + k; a.head = cnt + 20 + k;
-					int rc = RVB_OK;
-					if (k <= 1) rc = launch_map<256, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 6, kModeBack>(c, make_layout(1536, H, WPS, W, mcs, 0).total, n_split));
-					if (k == 2) rc = launch_map<256, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 8, kModeBack>(c, make_layout(2048, H, WPS, W, mcs, 0).total, n_split));
-					if (k == 3) rc = launch_map<512, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 6, kModeBack>(c, make_layout(3072, H, WPS, W, mcs, 0).total, n_split));
-					if (rc) return rc;
-				}
-				CU(cudaEventRecord(c->ev_join, mono_st));
+				if ((rc = launch_mono(split_chains ? 4 : 0, side))) return rc;
+				CU(cudaEventRecord(c->ev_join, side));
 				CU(cudaStreamWaitEvent(st, c->ev_join, 0));
 			}
 		}
@@ -1063,6 +1133,7 @@ extern "C" int rvb_debug_cluster_labels(rvb_ctx *c, const rvb_params *p, const u
 	CU(cudaMemcpyAsync(D + o_list, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
 	MapArgs a;
 	memset(&a, 0, sizeof(a));
+	a.force_class = -1;
 	a.maps_u8 = D + o_map; a.H = h; a.W = w; a.WPS = WPS; a.gstride = WPS;
 	a.list = (const int *)(D + o_list); a.head = (int *)(D + o_cnt); a.list_len = (int *)(D + o_cnt) + 1;
 	a.out = (MapOut *)(D + o_out); a.labels_dbg = (int32_t *)(D + o_lab);
