@@ -363,6 +363,19 @@ def gpu_arm(args, rank, world, local_rank):
 		sys.stderr.write('map kernel phase split (SM cycles summed over CTAs):\n')
 		for nme, v in zip(names, cyc):
 			sys.stderr.write('  %-20s %14d  %5.1f%%\n' % (nme, v, 100.0 * v / tot))
+	# what the link alone allows for the e2e entry: one plain pinned-host -> device copy of a step's maps
+	scratch_dev = torch.empty(NM * H * W, dtype=torch.uint8, device='cuda')
+	h2d_ms = None
+	for _ in range(3):
+		barrier()
+		eh0, eh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		eh0.record(streams[0])
+		scratch_dev.copy_(host_maps, non_blocking=True)
+		eh1.record(streams[0])
+		torch.cuda.synchronize()
+		t = eh0.elapsed_time(eh1)
+		h2d_ms = t if h2d_ms is None else min(h2d_ms, t)
+	del scratch_dev
 	frames_per_step = NF * R
 	value = world * frames_per_step * args.steps / (ms_dev / 1e3)
 	e2e = world * frames_per_step * args.steps / (ms_e2e / 1e3)
@@ -382,7 +395,7 @@ def gpu_arm(args, rank, world, local_rank):
 			traffic = prof.get('dram_bytes_per_step')
 		except Exception:
 			pass
-		cpu_v, cpu_cores, cpu_desc, _ = cpu_baseline(vds, args.cpu_sample) if world == 1 else (None, None, None, None)
+		cpu_v, cpu_cores, cpu_desc, _ = cpu_baseline(vds, args.cpu_sample) if (world == 1 and args.cpu_sample > 0) else (None, None, None, None)
 		line = {
 			'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
 			'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -395,10 +408,12 @@ def gpu_arm(args, rank, world, local_rank):
 					'value_entry': 'device-resident uint8 [N][140][256]', 'e2e_entry': 'pinned host uint8 [H][W][N] per clip',
 					'batches_in_flight': NCTX},
 			'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(NM * H * W), 'd2h_bytes_per_step': int(R * NF * 16),
-					'ms_per_step': ms_e2e / args.steps},
+					'ms_per_step': ms_e2e / args.steps,
+					'h2d_copy_alone_ms': h2d_ms, 'h2d_copy_alone_gbs': NM * H * W / (h2d_ms / 1e3) / 1e9,
+					'note': 'h2d_copy_alone_* = one plain cudaMemcpyAsync of the same pinned buffer: the floor the host link sets for an e2e step'},
 			'gpu_launches': int(launches_n),
 			'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-						'traffic': traffic, 'kernel': 'rvb::map_kernel<NT,TPT> (all capacity classes and waves of a step)',
+						'traffic': traffic, 'kernel': 'map pipeline of a step: rvb::map_kernel<256,16,Front> -> rvb::prim_kernel<NW,KMAX> x5 -> rvb::map_kernel<NT,TPT,Back> x5, cut-adjacent chains in rvb::map_kernel<NT,TPT,Mono> x5 on a side stream (joined before the end event)',
 						'algorithmic_bytes_per_step': algo, 'kernel_ms_per_step': map_ms / args.steps,
 						'kernel_launches_per_step': map_launches / args.steps,
 						'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'},

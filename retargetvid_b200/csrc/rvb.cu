@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <complex>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/retargetvid_b200.h"
@@ -101,6 +102,9 @@ struct rvb_ctx {
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
 	DevBuf scr_pinfo, scr_val, scr_pkey;
+	const void *nhw_zero_p = nullptr;   // maps_nhw was cleared at this address for this geometry
+	size_t nhw_zero_cap = 0;
+	int nhw_zero_w = 0, nhw_zero_wps = 0, nhw_zero_h = 0;
 	PinBuf stage, stage_out;
 };
 
@@ -478,6 +482,39 @@ static int occupancy_grid(rvb_ctx *c, int smem, int n_items) {
 }
 
 namespace {
+// Orders the host -> device uploads of all contexts of one device (see rvb_crop_track_batch).
+struct H2dGate {
+	static constexpr int kMaxDev = 64;
+	static std::mutex mu[kMaxDev];
+	static cudaEvent_t ev[kMaxDev];
+	int dev;
+	cudaStream_t st;
+	int rc = RVB_OK;
+	bool locked = false;
+	H2dGate(int device, cudaStream_t stream) : dev(device), st(stream) {
+		if (dev < 0 || dev >= kMaxDev) { dev = -1; return; }
+		mu[dev].lock();
+		locked = true;
+		if (ev[dev] == nullptr) {
+			if (cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) { rc = fail(RVB_ERR_CUDA, "cudaEventCreate (upload gate)"); return; }
+		} else if (cudaStreamWaitEvent(st, ev[dev], 0) != cudaSuccess) {
+			rc = fail(RVB_ERR_CUDA, "cudaStreamWaitEvent (upload gate)");
+		}
+	}
+	int done() {
+		int r = RVB_OK;
+		if (dev >= 0 && locked) {
+			if (cudaEventRecord(ev[dev], st) != cudaSuccess) r = fail(RVB_ERR_CUDA, "cudaEventRecord (upload gate)");
+			mu[dev].unlock();
+			locked = false;
+		}
+		return r;
+	}
+	~H2dGate() { if (locked) mu[dev].unlock(); }
+};
+std::mutex H2dGate::mu[H2dGate::kMaxDev];
+cudaEvent_t H2dGate::ev[H2dGate::kMaxDev] = {};
+
 struct Staging {  // packs the small per-call arrays into one pinned block -> one H2D copy
 	std::vector<uint8_t> bytes;
 	size_t add(const void *src, size_t n) {
@@ -725,6 +762,11 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		// gather into one device block (H2D from host memory, or D2D from per-clip device blocks)
 		if (c->maps_in.ensure((size_t)NM * bytes_per_map)) return RVB_ERR_CUDA;
 		const cudaMemcpyKind k = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+		// Host buffers: the big uploads of the contexts of one device go over the link one after the other.  Interleaved
+		// they all finish late and every context's kernels start late; in order, the first context computes while the
+		// second uploads (measured: 5 steps over 3 contexts, 26.2 -> see profiles/README.md).
+		H2dGate gate(host ? c->device : -1, st);
+		if (gate.rc) return gate.rc;
 		if (b->clip_maps) {
 			for (int i = 0; i < nc; ++i) {
 				if (!b->clip_maps[i]) return fail(RVB_ERR_INVALID, "clip_maps[%d] is NULL", i);
@@ -735,6 +777,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 			CU(cudaMemcpyAsync(c->maps_in.p, b->maps, (size_t)NM * bytes_per_map, k, st));
 		}
 		d_in = c->maps_in.p;
+		if (gate.done()) return RVB_ERR_CUDA;
 	}
 	if (b->maps_kind == RVB_MAPS_F32_NHW) {
 		d_f32 = (const float *)d_in;
@@ -745,12 +788,18 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	} else {
 		const uint8_t *src = (const uint8_t *)d_in;
 		if (c->maps_nhw.ensure((size_t)NM * H * WPS)) return RVB_ERR_CUDA;
-		CU(cudaMemsetAsync(c->maps_nhw.p, 0, (size_t)NM * H * WPS, st));
-		for (int i = 0; i < nc; ++i) {
-			const ClipDev &d = clips[i];
-			dim3 grid((d.n_maps + 31) / 32, (H * W + 31) / 32), block(32, 8);
-			transpose_hwn_kernel<<<grid, block, 0, st>>>(src + (size_t)d.map_offset * H * W, H, W, d.n_maps,
-														 (uint8_t *)c->maps_nhw.p + (size_t)d.map_offset * H * WPS, WPS);
+		// the padding columns x >= W must read 0; the transposition never writes them, so they are cleared only when
+		// the buffer is new or the geometry changed
+		if (c->nhw_zero_p != c->maps_nhw.p || c->nhw_zero_cap != c->maps_nhw.cap || c->nhw_zero_w != W || c->nhw_zero_wps != WPS || c->nhw_zero_h != H) {
+			CU(cudaMemsetAsync(c->maps_nhw.p, 0, c->maps_nhw.cap, st));
+			c->nhw_zero_p = c->maps_nhw.p; c->nhw_zero_cap = c->maps_nhw.cap; c->nhw_zero_w = W; c->nhw_zero_wps = WPS; c->nhw_zero_h = H;
+		}
+		int max_maps = 1;
+		for (int i = 0; i < nc; ++i) max_maps = std::max(max_maps, clips[i].n_maps);
+		for (int z0 = 0; z0 < nc; z0 += 65535) {
+			const int nz = std::min(nc - z0, 65535);
+			dim3 grid((max_maps + kTrMaps - 1) / kTrMaps, H, nz);
+			transpose_hwn_kernel<<<grid, 256, 0, st>>>(src, (size_t)NM * H * W, d_clips + z0, H, W, (uint8_t *)c->maps_nhw.p, WPS);
 			c->launches += 1;
 		}
 		CU(cudaGetLastError());

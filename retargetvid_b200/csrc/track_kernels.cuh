@@ -595,22 +595,74 @@ __global__ void clip_scores_kernel(const ClipDev *clips, int n_clips, const MapO
 	}
 }
 
-// [H][W][N] (reference layout, frame index fastest) -> [N][H][WPS]
-__global__ void transpose_hwn_kernel(const uint8_t *src, int H, int W, int N, uint8_t *dst, int WPS) {
-	__shared__ uint8_t tile[32][33];
-	// grid: x over N tiles, y over pixel tiles (pixel index p = y * W + x)
-	const int n0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
-	const int P = H * W;
-	for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-		const int p = p0 + i, n = n0 + threadIdx.x;
-		tile[i][threadIdx.x] = (p < P && n < N) ? src[(size_t)p * N + n] : 0;
+// [H][W][N] (reference layout, frame index fastest) -> [N][H][WPS], every clip of the batch in one launch.
+// The clips' [H][W][n_maps] blocks are packed back to back in src_all (clip i starts at map_offset * H * W).
+// One CTA moves one image row (W pixels) of kTrMaps consecutive maps of one clip:
+//   in : per pixel a run of <= 60 bytes at an arbitrary alignment -> half a warp reads the <= 16 aligned 32-bit words that
+//        cover it and scatters the bytes into the transposed shared tile (row stride 65 words: conflict-free);
+//   out: per map 250 contiguous bytes of a 256-byte-aligned row -> 32-bit shared loads, 128-byte coalesced stores.
+// grid: x over map tiles (fastest: the tiles of one pixel row share their cache lines), y = image row, z = clip.
+constexpr int kTrMaps = 60;
+constexpr int kTrStrideW = 65;   // words per tile row (>= WPS / 4 + 1, odd)
+
+__global__ void __launch_bounds__(256) transpose_hwn_kernel(const uint8_t *__restrict__ src_all, size_t src_bytes,
+															const ClipDev *__restrict__ clips, int H, int W,
+															uint8_t *__restrict__ dst, int WPS) {
+	__shared__ uint32_t tile32[kTrMaps * kTrStrideW];
+	uint8_t *tile = reinterpret_cast<uint8_t *>(tile32);
+	const ClipDev cd = clips[blockIdx.z];
+	const int N = cd.n_maps;
+	const int n0 = blockIdx.x * kTrMaps;
+	if (n0 >= N) return;
+	const int nb = min(kTrMaps, N - n0);
+	const int y = blockIdx.y;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int half = lane >> 4, hl = lane & 15;
+	const uintptr_t lo = reinterpret_cast<uintptr_t>(src_all), hi = lo + src_bytes;
+	const uintptr_t clip0 = lo + (size_t)cd.map_offset * H * W;
+	// ---- in ----
+	for (int x0 = warp * 2; x0 < W; x0 += 16 * 4) {
+		uint32_t w[4];
+		uintptr_t seg[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const int x = x0 + u * 16 + half;
+			seg[u] = clip0 + ((size_t)y * W + x) * N + n0;
+			const uintptr_t a = (seg[u] & ~(uintptr_t)3) + 4u * hl;
+			w[u] = 0;
+			if (x < W && a < seg[u] + nb) {
+				if (a >= lo && a + 4 <= hi) {
+					w[u] = __ldg(reinterpret_cast<const uint32_t *>(a));
+				} else {
+					for (int k = 0; k < 4; ++k)
+						if (a + k >= lo && a + k < hi) w[u] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(a + k)) << (8 * k);
+				}
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const int x = x0 + u * 16 + half;
+			if (x >= W) continue;
+			const int nl0 = (int)((long long)((seg[u] & ~(uintptr_t)3) + 4u * hl) - (long long)seg[u]);   // map index of byte 0
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const int nl = nl0 + k;
+				if (nl >= 0 && nl < nb) tile[(size_t)nl * (kTrStrideW * 4) + x] = (uint8_t)(w[u] >> (8 * k));
+			}
+		}
 	}
 	__syncthreads();
-	for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-		const int n = n0 + i, p = p0 + threadIdx.x;
-		if (p < P && n < N) {
-			const int y = p / W, x = p - y * W;
-			dst[((size_t)n * H + y) * WPS + x] = tile[threadIdx.x][i];
+	// ---- out ----
+	const int words = (W + 3) >> 2;          // the last word may carry up to 3 bytes of the padding columns
+	uint8_t *out = dst + ((size_t)(cd.map_offset + n0) * H + y) * WPS;
+	const size_t map_stride = (size_t)H * WPS;
+	for (int i = tid; i < nb * 64; i += 256) {
+		const int r = i >> 6, c = i & 63;
+		if (c < words) {
+			uint32_t v = tile32[r * kTrStrideW + c];
+			const int valid = W - 4 * c;     // bytes of this word that are pixels
+			if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+			*reinterpret_cast<uint32_t *>(out + (size_t)r * map_stride + 4 * c) = v;
 		}
 	}
 }
