@@ -40,9 +40,17 @@ def _make(spec):
 	return synth.make_clip(**spec)
 
 
-def make_workload(n_clips, rank):
-	from retargetvid_b200 import synth
-	specs = synth.config_clips(3, n_clips=n_clips, rank=rank)
+def make_workload(n_clips, rank, world=1, workload='c3'):
+	"""c3 (default): BASELINE.json configs[2], every rank its own n_clips clips (weak scaling).
+	c5: configs[4], ONE corpus of n_clips clips sharded per video over the ranks, longest first by map count
+	(retargetvid_b200/sharding.py); the map count follows from the frame count alone."""
+	from retargetvid_b200 import sharding, synth
+	if workload == 'c5':
+		specs = synth.config_clips(5, n_clips=n_clips)
+		costs = [len(synth.sampling_table(sp['fc'], sp.get('shot_starts', ()), 6)[0]) for sp in specs]
+		specs = [specs[i] for i in sharding.my_shard(costs, rank, world)]
+	else:
+		specs = synth.config_clips(3, n_clips=n_clips, rank=rank)
 	procs = min(len(specs), max(1, (os.cpu_count() or 1)))
 	if procs > 1:
 		with mp.get_context('fork').Pool(procs) as pool:
@@ -161,7 +169,11 @@ def gpu_arm(args, rank, world, local_rank):
 		import torch.distributed as dist
 		dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-	vds = make_workload(args.clips, rank)
+	global RATIOS
+	c5 = args.workload == 'c5'
+	if c5:
+		RATIOS = ['1:3', '3:1', '9:16', '4:5']
+	vds = make_workload(args.clips, rank, world, args.workload)
 	nc = len(vds)
 	R = len(RATIOS)
 	NM = sum(v['fc_sel'] for v in vds)
@@ -377,8 +389,13 @@ def gpu_arm(args, rank, world, local_rank):
 		h2d_ms = t if h2d_ms is None else min(h2d_ms, t)
 	del scratch_dev
 	frames_per_step = NF * R
-	value = world * frames_per_step * args.steps / (ms_dev / 1e3)
-	e2e = world * frames_per_step * args.steps / (ms_e2e / 1e3)
+	tot_frames, tot_maps, tot_clips = world * NF, world * NM, world * nc
+	if dist is not None and c5:      # ranks hold different shards of one corpus
+		t = torch.tensor([NF, NM, nc], device='cuda', dtype=torch.int64)
+		dist.all_reduce(t)
+		tot_frames, tot_maps, tot_clips = (int(x) for x in t.tolist())
+	value = tot_frames * R * args.steps / (ms_dev / 1e3)
+	e2e = tot_frames * R * args.steps / (ms_e2e / 1e3)
 	line = None
 	if rank == 0:
 		peaks = {}
@@ -398,12 +415,15 @@ def gpu_arm(args, rank, world, local_rank):
 		cpu_v, cpu_cores, cpu_desc, _ = cpu_baseline(vds, args.cpu_sample) if (world == 1 and args.cpu_sample > 0) else (None, None, None, None)
 		line = {
 			'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-			'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+			'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'strong' if c5 else 'weak', 'vs_baseline': None,
 			'dtype': 'u8 maps / int32 lattice arithmetic / f64 track', 'data': 'synthetic',
-			'config': {'workload': 'BASELINE.json configs[2]: %d synthetic DHF1K-shaped 640x360 clips per GPU x ratios %s, '
-								'default (ICIP-2021) crop params' % (nc, ','.join(RATIOS)),
+			'config': {'workload': ('BASELINE.json configs[4]: one corpus of %d synthetic DHF1K-shaped 640x360 clips sharded per video over %d GPU(s) '
+								'(longest first by map count) x ratios %s, default (ICIP-2021) crop params' % (tot_clips, world, ','.join(RATIOS))) if c5 else
+								('BASELINE.json configs[2]: %d synthetic DHF1K-shaped 640x360 clips per GPU x ratios %s, '
+								'default (ICIP-2021) crop params' % (nc, ','.join(RATIOS))),
+					'total_clips': tot_clips, 'total_frames': tot_frames, 'total_maps': tot_maps,
 					'clips_per_gpu': nc, 'frames_per_gpu': NF, 'maps_per_gpu': NM, 'ratios': RATIOS,
-					'maps_per_sec': world * NM * args.steps / (ms_dev / 1e3),
+					'maps_per_sec': tot_maps * args.steps / (ms_dev / 1e3),
 					'input_bytes_per_gpu': NM * H * WPS, 'l2': 'inputs larger than L2 (no flush needed)',
 					'value_entry': 'device-resident uint8 [N][140][256]', 'e2e_entry': 'pinned host uint8 [H][W][N] per clip',
 					'batches_in_flight': NCTX},
@@ -459,14 +479,19 @@ def main():
 	ap.add_argument('--steps', type=int, default=5)
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-	ap.add_argument('--clips', type=int, default=200, help='clips per GPU (BASELINE configs[2]: 200)')
+	ap.add_argument('--workload', default='c3', choices=['c3', 'c5'],
+					help='c3: BASELINE configs[2], --clips clips per GPU, 2 ratios, weak scaling (default, the metric is quoted on it); '
+						'c5: configs[4], one corpus of --clips clips (default 2000) sharded over the GPUs, 4 ratios, strong scaling')
+	ap.add_argument('--clips', type=int, default=None, help='clips per GPU (c3, default 200) or in the corpus (c5, default 2000)')
 	ap.add_argument('--cpu-sample', type=int, default=16, help='clips in the bounded CPU sample')
-	ap.add_argument('--streams', type=int, default=3, help='contexts/streams used to pipeline consecutive batches')
+	ap.add_argument('--streams', type=int, default=4, help='contexts/streams used to pipeline consecutive batches')
 	ap.add_argument('--phases', action='store_true', help='also print the per-phase SM-cycle split of the map kernel (stderr)')
 	args = ap.parse_args()
 	rank = int(os.environ.get('RANK', '0'))
 	world = int(os.environ.get('WORLD_SIZE', '1'))
 	local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+	if args.clips is None:
+		args.clips = 2000 if args.workload == 'c5' else 200
 	if args.impl == 'reference':
 		line = reference_arm(args, rank, world)
 	else:

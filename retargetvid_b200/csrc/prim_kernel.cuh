@@ -137,8 +137,11 @@ __device__ __forceinline__ void prim_seg_warps(uint2 *pinfo, uint32_t *lkey, uin
 	if constexpr (NW == 1) __syncwarp(); else __syncthreads();
 }
 
+// warps per SM the register budget allows: 24 slots -> 128 registers -> 16 warps, 16 slots -> 20, 12 slots -> 24
+__host__ __device__ constexpr int prim_warps_per_sm(int kmax) { return kmax >= 24 ? 16 : kmax >= 16 ? 20 : 24; }
+
 template <int NW, int KMAX>
-__global__ void __launch_bounds__(32 * NW, 16 / NW) prim_kernel(const PrimArgs a) {
+__global__ void __launch_bounds__(32 * NW, prim_warps_per_sm(KMAX) / NW) prim_kernel(const PrimArgs a) {
 	constexpr int NT = 32 * NW;
 	extern __shared__ __align__(16) uint8_t psm[];
 	__shared__ uint32_t wmin[2][32];

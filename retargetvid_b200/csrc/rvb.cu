@@ -99,6 +99,7 @@ struct rvb_ctx {
 	DevBuf phase;
 	bool chain_levels = false;  // RVB_CHAIN_LEVELS=1: chains go through the split pipeline one depth per launch; default: the
 	                            // monolithic kernel walks them on the side stream (measured 6 % faster at 3 batches in flight)
+	int prim_variant[4] = {0, 0, 0, 0};
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
 	DevBuf scr_pinfo, scr_val, scr_pkey;
@@ -111,6 +112,7 @@ struct rvb_ctx {
 // ---------------------------------------------------------------------------------------------
 // shared-memory layout of the map kernel for a capacity of nmax points
 // ---------------------------------------------------------------------------------------------
+static const int kPrimVariantDefault[4] = {0, 0, 0, 0};
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
 static const int kMaxDynSmem = 227 * 1024 - 1024;  // per-CTA opt-in limit minus the kernel's static shared memory
 
@@ -379,6 +381,10 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	{
 		const char *e = getenv("RVB_NO_SPLIT");
 		c->split = !(e && e[0] == '1');
+		// RVB_PRIM_VARIANT="abcd": per Prim size class 0..3, '1' selects the shape with more warps and fewer register
+		// slots per thread (<2,12> <4,12> <4,16> <8,12> instead of <1,24> <2,24> <4,24> <4,24>)
+		const char *v = getenv("RVB_PRIM_VARIANT");
+		for (int k = 0; k < 4; ++k) c->prim_variant[k] = (v && (int)strlen(v) > k && v[k] == '1') ? 1 : kPrimVariantDefault[k];
 	}
 	*out = c;
 	return RVB_OK;
@@ -470,6 +476,18 @@ static int launch_map(rvb_ctx *c, MapArgs a, int H, int W, int WPS, int grid, cu
 	c->launches += 1;
 	c->map_launches += 1;
 	return RVB_OK;
+}
+
+// one Prim launch: persistent CTAs of NW warps, as many per SM as the register budget of KMAX slots allows
+template <int NW, int KMAX>
+static void launch_prim(rvb_ctx *c, const PrimArgs &pa, int n_maps, int smem, cudaStream_t stream) {
+	static bool attr_set[64] = {};
+	if (c->device >= 0 && c->device < 64 && !attr_set[c->device]) {
+		cudaFuncSetAttribute(prim_kernel<NW, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+		attr_set[c->device] = true;
+	}
+	const int per_sm = prim_warps_per_sm(KMAX) / NW;
+	prim_kernel<NW, KMAX><<<std::min(n_maps, c->n_sm * per_sm), 32 * NW, smem, stream>>>(pa);
 }
 
 template <int NT, int TPT, int MODE = kModeMono>
@@ -921,10 +939,16 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 						const int smem = 12 * pa.cap;
 						// (warps per map, register slots per thread): 16 warps per SM in every class -- a warp issues at most
 						// every third cycle in this loop (half-rate integer pipe + dependent latency)
-						if (k == 0) prim_kernel<1, 24><<<std::min(ns, c->n_sm * 16), 32, smem, stream>>>(pa);
-						if (k == 1) prim_kernel<2, 24><<<std::min(ns, c->n_sm * 8), 64, smem, stream>>>(pa);
-						if (k == 2 || k == 3) prim_kernel<4, 24><<<std::min(ns, c->n_sm * 4), 128, smem, stream>>>(pa);
-						if (k == 4) prim_kernel<8, 16><<<std::min(ns, c->n_sm * 2), 256, smem, stream>>>(pa);
+						const int v = c->prim_variant[k];
+						if (k == 0 && v == 0) launch_prim<1, 24>(c, pa, ns, smem, stream);
+						if (k == 0 && v == 1) launch_prim<2, 12>(c, pa, ns, smem, stream);
+						if (k == 1 && v == 0) launch_prim<2, 24>(c, pa, ns, smem, stream);
+						if (k == 1 && v == 1) launch_prim<4, 12>(c, pa, ns, smem, stream);
+						if (k == 2 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
+						if (k == 2 && v == 1) launch_prim<4, 16>(c, pa, ns, smem, stream);
+						if (k == 3 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
+						if (k == 3 && v == 1) launch_prim<8, 12>(c, pa, ns, smem, stream);
+						if (k == 4) launch_prim<8, 16>(c, pa, ns, smem, stream);
 						CU(cudaGetLastError());
 						c->launches += 1;
 						c->map_launches += 1;
