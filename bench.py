@@ -388,6 +388,43 @@ def gpu_arm(args, rank, world, local_rank):
 		t = eh0.elapsed_time(eh1)
 		h2d_ms = t if h2d_ms is None else min(h2d_ms, t)
 	del scratch_dev
+	# stage 6 (IoU evaluation, retargetvid_eval.py:133-194) as its own streaming measurement: the step's frames tiled
+	# 16x (synthetic annotator boxes, 6 annotators), device-resident, exact 128-bit accumulation per (video, annotator)
+	iou = None
+	if rank == 0:
+		TILE, U = 16, 6
+		nv = nc * TILE
+		foff = np.zeros(nv + 1, dtype=np.int64)
+		foff[1:] = np.cumsum(np.tile(np.array([v['fc'] for v in vds], dtype=np.int64), TILE))
+		nev = np.tile(np.array([v['fc'] for v in vds], dtype=np.int32), TILE)
+		nfi = int(foff[-1])
+		method = dev_boxes[0].repeat(TILE, 1).contiguous()
+		g = torch.Generator(device='cuda').manual_seed(7)
+		x1 = torch.randint(0, 500, (U, nfi, 1), device='cuda', generator=g, dtype=torch.int32)
+		y1 = torch.zeros((U, nfi, 1), device='cuda', dtype=torch.int32)
+		annot = torch.cat([x1, y1, x1 + 120, y1 + 360], dim=2).contiguous()
+		acc = torch.zeros((nv, U, 2), dtype=torch.int64, device='cuda')
+		ib = _cabi.rvb_iou_batch()
+		ib.n_videos, ib.n_users, ib.mem_space = nv, U, _cabi.RVB_MEM_DEVICE
+		ib.frame_offset = foff.ctypes.data
+		ib.n_eval = nev.ctypes.data
+		ib.method_boxes, ib.annot_boxes, ib.frame_iou, ib.acc = method.data_ptr(), annot.data_ptr(), None, acc.data_ptr()
+		for _ in range(3):
+			ctx.iou_batch(ib)
+		torch.cuda.synchronize()
+		ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		ei0.record(streams[0])
+		for _ in range(args.steps):
+			ctx.iou_batch(ib)
+		ei1.record(streams[0])
+		torch.cuda.synchronize()
+		iou_ms = ei0.elapsed_time(ei1) / args.steps
+		iou_bytes = nfi * (16 + 16 * U)
+		iou = {'what': 'rvb_iou_batch_run (iou_kernel): %d frames x %d annotators per call, device-resident boxes, one call per step '
+						'(includes the per-call frame->video table upload)' % (nfi, U),
+				'ious_per_sec': nfi * U / (iou_ms / 1e3), 'ms_per_call': iou_ms, 'algorithmic_bytes_per_call': iou_bytes,
+				'achieved_gbs': iou_bytes / (iou_ms / 1e3) / 1e9}
+		del method, annot, acc
 	frames_per_step = NF * R
 	tot_frames, tot_maps, tot_clips = world * NF, world * NM, world * nc
 	if dist is not None and c5:      # ranks hold different shards of one corpus
@@ -442,8 +479,12 @@ def gpu_arm(args, rank, world, local_rank):
 										'frac': NM * ALGO_BYTES_PER_MAP * args.steps / (stream_map_ms / 1e3) / 1e9 / peak,
 										'kernel_ms_per_step': stream_map_ms / args.steps, 'ms_per_step': stream_ms / args.steps,
 										'frames_per_sec': frames_per_step * args.steps / (stream_ms / 1e3)},
+			'iou_stage': iou,
 			'clocks': clocks,
 		}
+		if iou is not None:
+			iou['peak_gbs'] = peak
+			iou['frac'] = iou['achieved_gbs'] / peak
 		if cpu_v is not None:
 			line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cpu_cores, 'kind': 'port', 'sample': cpu_desc}
 	if dist is not None:
