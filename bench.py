@@ -315,6 +315,8 @@ def gpu_arm(args, rank, world, local_rank):
 			raise errs[0]
 		return reduce_max(e0.elapsed_time(e1))
 
+	stage_ms = [0.0, 0.0, 0.0, 0.0]
+
 	def timed_map_kernel(steps):
 		"""the dominant kernel alone: one context, its own CUDA events around the map-kernel launches"""
 		barrier()
@@ -324,8 +326,36 @@ def gpu_arm(args, rank, world, local_rank):
 			ms, nl = ctx.last_map_kernel_ms()
 			map_ms += ms
 			map_launches += nl
+			for i, v in enumerate(ctx.last_stage_ms()):
+				stage_ms[i] += v / steps
 		barrier()
 		return map_ms, map_launches
+
+	def prim_pairs():
+		"""Point-pair updates of the Prim launches of one step: sum of n(n-1)/2 over the maps of the split pipeline (the
+		maps outside cut-adjacent chains, smartVidCrop.py:2369-2373, with at most 4096 points), n from the library's own
+		per-map record."""
+		info = torch.empty((NM, 4), dtype=torch.int32, device='cuda')
+		bb = batch(True, 0)
+		bb.map_info = info.data_ptr()
+		ctx.crop_track_batch(params, bb)
+		torch.cuda.synchronize()
+		npts = info[:, 0].cpu().numpy().astype(np.int64)
+		in_chain = np.zeros(NM, dtype=bool)
+		mo = 0
+		for vd in vds:
+			n = vd['fc_sel']
+			cut = np.zeros(n + 2, dtype=bool)
+			sel = np.asarray(vd['segmentation_sel'])
+			cut[sel[:, 0]] = True
+			cut[sel[-1, 1]] = True
+			for k in range(n - 2):
+				if (k >= 1 and cut[k - 1]) or cut[k] or cut[k + 1]:
+					in_chain[mo + k] = in_chain[mo + k + 1] = True
+			mo += n
+		keep = (~in_chain) & (npts <= 4096) & (npts > CP['hdbscan_min'] + 1)
+		n = npts[keep]
+		return int((n * (n - 1) // 2).sum()), int(keep.sum())
 
 	for _ in range(args.warmup):
 		for k in range(NCTX):
@@ -348,6 +378,7 @@ def gpu_arm(args, rank, world, local_rank):
 	# roofline of the dominant kernel (the fused map kernel family): separate un-pipelined pass
 	map_ms, map_launches = timed_map_kernel(args.steps)
 
+	pairs, pair_maps = prim_pairs() if rank == 0 else (0, 0)
 	# (i) of SURVEY.md H2: the streaming stages alone (threshold, mean saliency, centroid, track, boxes), i.e. the
 	# same call with the clustering filter switched off -- this is the part of the path that is HBM-bound
 	CP_s = dict(CP)
@@ -479,9 +510,20 @@ def gpu_arm(args, rank, world, local_rank):
 										'frac': NM * ALGO_BYTES_PER_MAP * args.steps / (stream_map_ms / 1e3) / 1e9 / peak,
 										'kernel_ms_per_step': stream_map_ms / args.steps, 'ms_per_step': stream_ms / args.steps,
 										'frames_per_sec': frames_per_step * args.steps / (stream_ms / 1e3)},
+			'prim_stage': None,
 			'iou_stage': iou,
 			'clocks': clocks,
 		}
+		if stage_ms[1] > 0 and clocks and clocks.get('sm_mhz'):
+			# the Prim loop is bound by the integer-ALU pipe, not by HBM: 3.5 half-rate instructions per 32 point pairs
+			# = 7 cycles per SMSP (profiles/r01za_int_pipe_ubench.txt)
+			n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+			pipe_peak = n_sm * 4 * clocks['sm_mhz'] * 1e6 * 32 / 7.0
+			ach = pairs / (stage_ms[1] / 1e3)
+			line['prim_stage'] = {'what': 'rvb::prim_kernel x5 of one step, CUDA events on the launching stream (the side stream with the chain maps runs beside it)',
+								'bound': 'integer ALU pipe (VABSDIFF4 / VIMNMX / VIMNMX3 at half rate)', 'maps': pair_maps, 'point_pair_updates_per_step': pairs,
+								'ms_per_step': stage_ms[1], 'achieved': ach, 'peak': pipe_peak, 'unit': 'pair updates/s', 'frac': ach / pipe_peak,
+								'front_ms_per_step': stage_ms[0], 'back_ms_per_step': stage_ms[2], 'map_pipeline_ms_per_step': stage_ms[3]}
 		if iou is not None:
 			iou['peak_gbs'] = peak
 			iou['frac'] = iou['achieved_gbs'] / peak
@@ -517,7 +559,7 @@ def reference_arm(args, rank, world):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('--gpus', type=int, default=1)
-	ap.add_argument('--steps', type=int, default=5)
+	ap.add_argument('--steps', type=int, default=10)
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--workload', default='c3', choices=['c3', 'c5'],

@@ -151,6 +151,9 @@ int64_t rvb_ctx_launch_count(const rvb_ctx *ctx);
 /* CUDA-event time (ms) and launches of the dominant kernel (the fused map
  * kernel) summed over the last crop_track call; valid after a synchronise */
 int rvb_ctx_last_map_kernel_ms(rvb_ctx *ctx, float *ms, int32_t *launches);
+/* split pipeline of the last crop_track call, CUDA-event times (ms) on the launching stream:
+ * out = {front launch, Prim launches, back launches, whole map pipeline incl. the joined side stream} */
+int rvb_ctx_last_stage_ms(rvb_ctx *ctx, float out[4]);
 
 /* profiling aid: when enabled, the map kernel accumulates SM cycles per phase (11 phases: load, threshold+compact,
  * core distances, Prim, argsort emulation, Cartesian tree, condensed-tree BFS, fall-out, EOM+labels, rebuild+closing,

@@ -28,7 +28,7 @@ RVB_MAPS_U8_HWN = 1
 RVB_MAPS_F32_NHW = 2
 
 EXPORTS = ['rvb_version', 'rvb_last_error', 'rvb_ctx_create', 'rvb_ctx_destroy', 'rvb_ctx_set_stream',
-		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_params_default',
+		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_ctx_last_stage_ms', 'rvb_params_default',
 		'rvb_crop_track_batch', 'rvb_iou_batch_run', 'rvb_iou_mean_from_acc', 'rvb_debug_cluster_labels',
 		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles']
 
@@ -97,6 +97,7 @@ def load_library():
 	lib.rvb_ctx_launch_count.argtypes = [C.c_void_p]
 	lib.rvb_ctx_launch_count.restype = C.c_int64
 	lib.rvb_ctx_last_map_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+	lib.rvb_ctx_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
 	lib.rvb_params_default.argtypes = [C.POINTER(rvb_params), C.c_int]
 	lib.rvb_ctx_phase_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
 	lib.rvb_crop_track_batch.argtypes = [C.c_void_p, C.POINTER(rvb_params), C.POINTER(rvb_batch)]
@@ -177,6 +178,12 @@ class Context(object):
 
 	def launch_count(self):
 		return int(self.lib.rvb_ctx_launch_count(self.handle))
+
+	def last_stage_ms(self):
+		"""(front, Prim, back, whole map pipeline) CUDA-event ms of the last crop_track call (split pipeline)"""
+		out = (C.c_float * 4)()
+		check(self.lib.rvb_ctx_last_stage_ms(self.handle, out))
+		return [float(x) for x in out]
 
 	def last_map_kernel_ms(self):
 		ms = C.c_float()

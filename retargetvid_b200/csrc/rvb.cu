@@ -91,6 +91,8 @@ struct rvb_ctx {
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_map0 = nullptr, ev_map1 = nullptr, ev_stage = nullptr;
+	cudaEvent_t ev_st[3] = {nullptr, nullptr, nullptr};   // split pipeline, main stream: after front / Prim / back of set 0
+	bool stages_timed = false;
 	bool stage_busy = false;
 	bool map_timed = false;
 	int map_launches = 0;
@@ -347,6 +349,7 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	c->stream = c->own_stream;
 	CU(cudaEventCreate(&c->ev_map0));
 	CU(cudaEventCreate(&c->ev_map1));
+	for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&c->ev_st[i]));
 	CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
 	{
 		// experiment knobs (profiling only): RVB_SIDE_PRIO = CUDA priority of the side stream, RVB_CHAIN_LEVELS=1
@@ -401,6 +404,7 @@ extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
 	c->stage_out.release();
 	if (c->ev_map0) cudaEventDestroy(c->ev_map0);
 	if (c->ev_map1) cudaEventDestroy(c->ev_map1);
+	for (int i = 0; i < 3; ++i) if (c->ev_st[i]) cudaEventDestroy(c->ev_st[i]);
 	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -433,6 +437,17 @@ extern "C" int rvb_ctx_last_map_kernel_ms(rvb_ctx *c, float *ms, int32_t *launch
 	CU(cudaEventElapsedTime(&t, c->ev_map0, c->ev_map1));
 	if (ms) *ms = t;
 	if (launches) *launches = c->map_launches;
+	return RVB_OK;
+}
+
+extern "C" int rvb_ctx_last_stage_ms(rvb_ctx *c, float out[4]) {
+	if (!c || !out) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (!c->map_timed || !c->stages_timed) return fail(RVB_ERR_INVALID, "the last crop_track call did not run the split pipeline");
+	CU(cudaEventSynchronize(c->ev_map1));
+	CU(cudaEventElapsedTime(&out[0], c->ev_map0, c->ev_st[0]));
+	CU(cudaEventElapsedTime(&out[1], c->ev_st[0], c->ev_st[1]));
+	CU(cudaEventElapsedTime(&out[2], c->ev_st[1], c->ev_st[2]));
+	CU(cudaEventElapsedTime(&out[3], c->ev_map0, c->ev_map1));
 	return RVB_OK;
 }
 
@@ -855,6 +870,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.t_threshold = p->t_threshold; a.clust_filt = p->clust_filt; a.mcs = p->hdbscan_min;
 	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
 	c->map_launches = 0;
+	c->stages_timed = false;
 	CU(cudaEventRecord(c->ev_map0, st));
 	const bool streaming = !p->clust_filt && !rzs.on && !p->exit_on_low_cvrg && !keep_all_maps && d_u8 != nullptr &&
 						   (gstride % 16) == 0 && (((uintptr_t)d_u8) & 15) == 0;
@@ -953,6 +969,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 						c->launches += 1;
 						c->map_launches += 1;
 					}
+					if (set == 0) CU(cudaEventRecord(c->ev_st[1], stream));
 					a.ovf_list = nullptr; a.ovf_len = nullptr;
 					for (int k = k_first; k < kSplitClasses; ++k) {
 						a.list = lists + (size_t)k * ns; a.list_len = sc + 2 + k; a.head = sc + 2 + 2 * kSplitClasses + k;
@@ -969,10 +986,13 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				// long dependencies), then whatever overflowed into the monolithic kernel.
 				int rc = launch_front(0, st);
 				if (rc) return rc;
+				CU(cudaEventRecord(c->ev_st[0], st));
 				cudaStream_t side = getenv("RVB_NO_SIDE") ? st : c->side_stream;
 				CU(cudaEventRecord(c->ev_fork, st));
 				CU(cudaStreamWaitEvent(side, c->ev_fork, 0));
 				if ((rc = launch_prim_back(0, st))) return rc;
+				CU(cudaEventRecord(c->ev_st[2], st));
+				c->stages_timed = !sets[0].empty();
 				for (int k = 1; k < n_sets; ++k) {
 					if ((rc = launch_front(k, side))) return rc;
 					if ((rc = launch_prim_back(k, side))) return rc;

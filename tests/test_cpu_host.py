@@ -195,3 +195,23 @@ def test_cv_resize_restatement_matches_opencv():
 			assert np.array_equal(cv2.resize(a, (W, H), interpolation=cv2.INTER_LINEAR), cv_resize.resize_linear_u8(a, dsize_wh=(W, H)))
 			assert np.array_equal(cv2.resize(m, None, fx=1.0 / f, fy=1.0 / f, interpolation=cv2.INTER_NEAREST),
 								cv_resize.resize_nearest_u8(m, 1.0 / f, 1.0 / f))
+
+
+def test_bench_c5_shards_partition_the_corpus():
+	"""bench.py --workload c5 (BASELINE configs[4]): the ranks' shards are disjoint, cover the corpus and are
+	balanced by map count (per-video sharding, no collective)."""
+	sys.path.insert(0, ROOT)
+	import bench
+	from retargetvid_b200 import sharding, synth
+	specs = synth.config_clips(5, n_clips=64)
+	costs = [len(synth.sampling_table(sp['fc'], sp.get('shot_starts', ()), 6)[0]) for sp in specs]
+	world = 4
+	shards = sharding.lpt_shards(costs, world)
+	assert sorted(i for sh in shards for i in sh) == list(range(64))
+	loads = [sum(costs[i] for i in sh) for sh in shards]
+	assert max(loads) - min(loads) <= max(costs)
+	vds = bench.make_workload(16, 1, 2, 'c5')
+	want = [synth.config_clips(5, n_clips=16)[i] for i in sharding.my_shard(
+		[len(synth.sampling_table(sp['fc'], (), 6)[0]) for sp in synth.config_clips(5, n_clips=16)], 1, 2)]
+	assert [v['fc'] for v in vds] == [sp['fc'] for sp in want]
+	assert all(v['fc_sel'] == len(synth.sampling_table(v['fc'], (), 6)[0]) for v in vds)
