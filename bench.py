@@ -575,14 +575,22 @@ def main():
 	local_rank = int(os.environ.get('LOCAL_RANK', '0'))
 	if args.clips is None:
 		args.clips = 2000 if args.workload == 'c5' else 200
+	# the contract is ONE JSON line on stdout: anything a library prints there meanwhile (NCCL announces its version on
+	# stdout) goes to stderr instead
+	sys.stdout.flush()
+	saved_stdout = os.dup(1)
+	os.dup2(2, 1)
 	if args.impl == 'reference':
 		line = reference_arm(args, rank, world)
 	else:
 		if args.warmup < 3:
 			args.warmup = 3
 		line = gpu_arm(args, rank, world, local_rank)
+	sys.stdout.flush()
+	os.dup2(saved_stdout, 1)
+	os.close(saved_stdout)
 	if rank == 0 and line is not None:
-		print(json.dumps(line))
+		print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':

@@ -65,8 +65,25 @@ __device__ __forceinline__ void prim_steps(uint32_t (&pxy)[KMAX], uint32_t (&pc)
 			const uint32_t par = (uint32_t)(step & 1) * 128u;   // wmin[step & 1]
 			sts_u32(a_wm_mine + par, g);
 			__syncthreads();
-			g = lds_u32(a_wm_lane + par);   // lanes >= NW re-read the last entry: harmless for a minimum
-			g = __reduce_min_sync(0xffffffffu, g);
+			// every lane reads all NW warp minima with one or two broadcast vector loads: no second warp reduction on
+			// the per-step critical path
+			if constexpr (NW == 2) {
+				uint32_t v0, v1;
+				asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(a_wm + par) : "memory");
+				g = min(v0, v1);
+			} else if constexpr (NW == 4) {
+				uint32_t v0, v1, v2, v3;
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a_wm + par) : "memory");
+				g = min(min(v0, v1), min(v2, v3));
+			} else if constexpr (NW == 8) {
+				uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a_wm + par) : "memory");
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7) : "r"(a_wm + par + 16u) : "memory");
+				g = min(min(min(v0, v1), min(v2, v3)), min(min(v4, v5), min(v6, v7)));
+			} else {
+				g = lds_u32(a_wm_lane + par);   // lanes >= NW re-read the last entry: harmless for a minimum
+				g = __reduce_min_sync(0xffffffffu, g);
+			}
 		}
 		const uint32_t cu = g & kKeyIdxMask;
 		cur = (int)cu;
@@ -144,7 +161,7 @@ template <int NW, int KMAX>
 __global__ void __launch_bounds__(32 * NW, prim_warps_per_sm(KMAX) / NW) prim_kernel(const PrimArgs a) {
 	constexpr int NT = 32 * NW;
 	extern __shared__ __align__(16) uint8_t psm[];
-	__shared__ uint32_t wmin[2][32];
+	__shared__ __align__(16) uint32_t wmin[2][32];
 	__shared__ int s_map, s_live;
 	uint2 *pinfo = reinterpret_cast<uint2 *>(psm);
 	uint32_t *lkey = reinterpret_cast<uint32_t *>(psm + (size_t)8 * a.cap);
