@@ -156,6 +156,25 @@ class ClockSampler(object):
 		return out
 
 
+def bind_near_gpu(index):
+	"""Pins this process (and the threads and pinned buffers it creates from now on) to the CPUs NVML reports as local
+	to the GPU, so that the e2e uploads do not cross the socket interconnect.  Returns the number of CPUs kept."""
+	try:
+		import pynvml
+		import torch
+		pynvml.nvmlInit()
+		pr = torch.cuda.get_device_properties(index)
+		try:
+			bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+			h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+		except Exception:
+			h = pynvml.nvmlDeviceGetHandleByIndex(index)
+		pynvml.nvmlDeviceSetCpuAffinity(h)
+		return len(os.sched_getaffinity(0))
+	except Exception:
+		return None
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -174,6 +193,8 @@ def gpu_arm(args, rank, world, local_rank):
 	if c5:
 		RATIOS = ['1:3', '3:1', '9:16', '4:5']
 	vds = make_workload(args.clips, rank, world, args.workload)
+	all_cpus = os.sched_getaffinity(0)
+	near_cpus = None if args.no_bind else bind_near_gpu(local_rank)
 	nc = len(vds)
 	R = len(RATIOS)
 	NM = sum(v['fc_sel'] for v in vds)
@@ -480,6 +501,7 @@ def gpu_arm(args, rank, world, local_rank):
 			traffic = prof.get('dram_bytes_per_step')
 		except Exception:
 			pass
+		os.sched_setaffinity(0, all_cpus)      # the CPU arm gets every host core back
 		cpu_v, cpu_cores, cpu_desc, _ = cpu_baseline(vds, args.cpu_sample) if (world == 1 and args.cpu_sample > 0) else (None, None, None, None)
 		line = {
 			'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -498,6 +520,7 @@ def gpu_arm(args, rank, world, local_rank):
 			'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(NM * H * W), 'd2h_bytes_per_step': int(R * NF * 16),
 					'ms_per_step': ms_e2e / args.steps,
 					'h2d_copy_alone_ms': h2d_ms, 'h2d_copy_alone_gbs': NM * H * W / (h2d_ms / 1e3) / 1e9,
+					'cpus_near_gpu': near_cpus,
 					'note': 'h2d_copy_alone_* = one plain cudaMemcpyAsync of the same pinned buffer: the floor the host link sets for an e2e step'},
 			'gpu_launches': int(launches_n),
 			'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
@@ -568,6 +591,7 @@ def main():
 	ap.add_argument('--clips', type=int, default=None, help='clips per GPU (c3, default 200) or in the corpus (c5, default 2000)')
 	ap.add_argument('--cpu-sample', type=int, default=16, help='clips in the bounded CPU sample')
 	ap.add_argument('--streams', type=int, default=4, help='contexts/streams used to pipeline consecutive batches')
+	ap.add_argument('--no-bind', action='store_true', help='do not pin the process to the CPUs local to its GPU')
 	ap.add_argument('--phases', action='store_true', help='also print the per-phase SM-cycle split of the map kernel (stderr)')
 	args = ap.parse_args()
 	rank = int(os.environ.get('RANK', '0'))
