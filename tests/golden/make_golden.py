@@ -133,6 +133,14 @@ CLIPS = {
 	'border': (dict(seed=2010, fc=120), dict(t_border=10), ['1:3', '3:1']),
 	'best_settings': (dict(seed=2012, fc=240, shot_starts=[100]), 'BEST', ['1:3', '3:1']),
 	'best_hd_fr25': (dict(seed=2013, fc=150, w_orig=1920, h_orig=1080, fr=25.0), 'BEST', ['9:16']),
+	# parameters no other fixture moves: time shift, degree-1 LOESS with a 1 s window, a 3rd-order low-pass at 3 Hz
+	'shift_deg1': (dict(seed=2014, fc=200, shot_starts=[90]),
+					dict(shift_time=5, loess_degree=1, loess_w_secs=1, lp_order=3, lp_cutoff=3), ['1:3', '4:5']),
+	# clustering on a 4x down-scaled copy taken with INTER_NEAREST (resize_type 3)
+	'resize_nearest': (dict(seed=2015, fc=120, shot_starts=[50]),
+					dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=4, resize_type=3, select_sum=1), ['3:1']),
+	# a different sampling table: every 3rd frame gets a map, 24 fps
+	'skip3_fr24': (dict(seed=2016, fc=150, fr=24.0, skip=3, shot_starts=[75]), {}, ['9:16']),
 }
 
 
