@@ -477,6 +477,22 @@ def gpu_arm(args, rank, world, local_rank):
 				'ious_per_sec': nfi * U / (iou_ms / 1e3), 'ms_per_call': iou_ms, 'algorithmic_bytes_per_call': iou_bytes,
 				'achieved_gbs': iou_bytes / (iou_ms / 1e3) / 1e9}
 		del method, annot, acc
+	# BASELINE.json configs[0]: ONE 300-frame clip through the drop-in python entry point (host numpy maps in, boxes out)
+	c1 = None
+	if rank == 0:
+		from retargetvid_b200 import synth
+		vd1 = synth.make_clip(**synth.config_clips(1)[0])
+		CP1 = svc.sc_init_crop_params()
+		CP1['out_ratio'] = '1:3'
+		lat = []
+		for i in range(13):
+			t0 = time.perf_counter()
+			VD1, _res = svc.smart_vid_crop('c1.mp4', CP1, save_vid=False, vid_data=dict(vd1), device=local_rank)
+			lat.append((time.perf_counter() - t0) * 1e3)
+		lat = sorted(lat[3:])
+		c1 = {'what': 'configs[0]: smart_vid_crop() on one 640x360 clip of %d frames (%d maps), ratio 1:3, wall clock of the python call, '
+					'median of 10 after 3 warm-up calls' % (vd1['fc'], vd1['fc_sel']),
+				'ms_per_clip': lat[len(lat) // 2], 'frames_per_sec': vd1['fc'] / (lat[len(lat) // 2] / 1e3)}
 	frames_per_step = NF * R
 	tot_frames, tot_maps, tot_clips = world * NF, world * NM, world * nc
 	if dist is not None and c5:      # ranks hold different shards of one corpus
@@ -533,6 +549,7 @@ def gpu_arm(args, rank, world, local_rank):
 										'frac': NM * ALGO_BYTES_PER_MAP * args.steps / (stream_map_ms / 1e3) / 1e9 / peak,
 										'kernel_ms_per_step': stream_map_ms / args.steps, 'ms_per_step': stream_ms / args.steps,
 										'frames_per_sec': frames_per_step * args.steps / (stream_ms / 1e3)},
+			'single_clip': c1,
 			'prim_stage': None,
 			'iou_stage': iou,
 			'clocks': clocks,

@@ -1107,16 +1107,21 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	const long long NF = b->frame_offset[V];
 	if (NF < 1 || b->frame_offset[0] != 0) return fail(RVB_ERR_INVALID, "frame_offset must start at 0");
 	if (NF > 0x7fffffffLL) return fail(RVB_ERR_INVALID, "more than 2^31 frames in one call");
-	std::vector<int> first(V), neval(V);
+	std::vector<int> first(V + 1), neval(V);
+	long long max_frames = 1;
 	for (int v = 0; v < V; ++v) {
 		const long long f0 = b->frame_offset[v], f1 = b->frame_offset[v + 1];
 		if (f1 < f0) return fail(RVB_ERR_INVALID, "frame_offset not monotone");
 		if (b->n_eval[v] < 1 || b->n_eval[v] > f1 - f0) return fail(RVB_ERR_INVALID, "video %d: n_eval=%d of %lld frames", v, b->n_eval[v], f1 - f0);
 		first[v] = (int)f0;
 		neval[v] = b->n_eval[v];
+		max_frames = std::max(max_frames, f1 - f0);
 	}
 	Staging sg;
-	const size_t o_first = sg.add(first.data(), (size_t)V * sizeof(int));
+	first[V] = (int)NF;
+	const long long chunks = (max_frames + 255) / 256;
+	if (chunks > 65535) return fail(RVB_ERR_INVALID, "a video of %lld frames (max 16.7 M per video)", max_frames);
+	const size_t o_first = sg.add(first.data(), (size_t)(V + 1) * sizeof(int));
 	const size_t o_ne = sg.add(neval.data(), (size_t)V * sizeof(int));
 	const size_t o_acc = sg.add(nullptr, (size_t)V * U * 2 * sizeof(uint64_t));
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
@@ -1142,8 +1147,7 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	}
 	unsigned long long *d_acc = (unsigned long long *)(M + o_acc);
 	CU(cudaMemsetAsync(d_acc, 0, (size_t)V * U * 2 * sizeof(uint64_t), st));
-	const long long total = NF * U;
-	iou_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(d_method, d_annot, V, (const int *)(M + o_first),
+	iou_kernel<<<dim3((unsigned)V, (unsigned)chunks), 256, 0, st>>>(d_method, d_annot, (const int *)(M + o_first),
 															(const int *)(M + o_ne), NF, U, d_fiou, d_acc);
 	CU(cudaGetLastError());
 	c->launches += 1;

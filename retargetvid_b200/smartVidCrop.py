@@ -11,7 +11,6 @@ cache (``temp_path/<video>.pkl``, :2244-2256) or is passed directly.
 All arithmetic is done by the CUDA library through ``retargetvid_b200._cabi``;
 there is no CPU fallback.
 """
-import gc
 import os
 import pickle
 import time
@@ -137,20 +136,20 @@ def _fill_vd(VD, CP, res, ratio_index, want_smaps):
 	VD['mean_sal_scores'] = np.array(res.map_scores)
 	VD['mean_sal_score'] = res.mean_sal_score if CP['exit_on_spread_sal'] else None
 	VD['mean_cvrg_score'] = float(res.cvrg_scores[ratio_index]) if CP['exit_on_low_cvrg'] else None
-	dx = [float(v) for v in res.dx]
-	dy = [float(v) for v in res.dy]
+	dx = np.asarray(res.dx, dtype=np.float64).tolist()
+	dy = np.asarray(res.dy, dtype=np.float64).tolist()
 	VD['dx'] = dx
 	VD['dy'] = dy
-	VD['dxnf'] = [float(v) for v in res.dxnf]
-	VD['dynf'] = [float(v) for v in res.dynf]
-	jumps = [float(v) for v in res.jumps]
+	VD['dxnf'] = np.asarray(res.dxnf, dtype=np.float64).tolist()
+	VD['dynf'] = np.asarray(res.dynf, dtype=np.float64).tolist()
+	jumps = np.asarray(res.jumps, dtype=np.float64).tolist()
 	VD['jumps'] = [255 if v == 255.0 else v for v in jumps]
 	VD['jumps_inds'] = [i for i in range(1, len(jumps)) if CP['focus_stability'] and jumps[i] < CP['foces_stab_t']]
 	s = res.series
-	VD['dxi'] = [float(v) for v in s[0]]
-	VD['dyi'] = [float(v) for v in s[1]]
-	VD['dxl'] = [float(v) for v in s[2]]
-	VD['dyl'] = [float(v) for v in s[3]]
+	VD['dxi'] = s[0].tolist()
+	VD['dyi'] = s[1].tolist()
+	VD['dxl'] = s[2].tolist()
+	VD['dyl'] = s[3].tolist()
 	# sc_compute_bb truncates dxs/dys in place to original-size ints (smartVidCrop.py:995-999)
 	scale_h = float(VD['h_process']) / float(VD['h_orig'])
 	scale_w = float(VD['w_process']) / float(VD['w_orig'])
@@ -160,7 +159,7 @@ def _fill_vd(VD, CP, res, ratio_index, want_smaps):
 	for seg in np.asarray(VD['segmentation']):
 		ts += list(range(int(seg[1]) - int(seg[0]) + 1))
 	VD['ts'] = ts
-	VD['bbs'] = [[int(v) for v in bb] for bb in res.boxes[ratio_index]]
+	VD['bbs'] = np.asarray(res.boxes[ratio_index]).tolist()      # python ints, [x1, y1, x2, y2] per frame
 	if want_smaps and res.filtered is not None:
 		VD['smaps'] = np.ascontiguousarray(np.transpose(res.filtered, (1, 2, 0)))
 	return VD
@@ -276,7 +275,8 @@ def smart_vid_crop(video_path, CP=None,
 		print(' Times::')
 		for k, v in t_dict.items():
 			print('   %-21s : %s' % (k, v))
-	gc.collect()
+	# (the reference ends with gc.collect() to drop its frame buffers, smartVidCrop.py:2612; nothing of that size lives here
+	# and a full collection costs more than the whole GPU pass of a clip)
 	return VD, smart_crop_results
 
 
