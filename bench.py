@@ -125,7 +125,7 @@ class ClockSampler(object):
 				'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
 				'clocks_event_reasons.sw_power_cap')
 			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-										'--format=csv,noheader,nounits', '-lms', '100'],
+										'--format=csv,noheader,nounits', '-lms', '20'],
 										stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
 		except Exception:
 			self.proc = None
