@@ -30,10 +30,13 @@ class CropEngine(object):
 	def close(self):
 		self.ctx.close()
 
-	def run(self, vds, CP, ratios, detail=True, want_filtered=False, cvrg_window='reference', raise_on_clip_error=True):
+	def run(self, vds, CP, ratios, detail=True, want_filtered=False, cvrg_window='reference', raise_on_clip_error=True,
+			np_int=False):
 		"""vds: list of vid_data dicts; ratios: list of 'a:b' strings.
+		np_int: focus stability samples diagonal moves as the reference does on the numpy it pins (np.int exists,
+		smartVidCrop.py:1377,1384) instead of returning 255 for them as it does on numpy >= 1.24.
 		Returns a list of ClipResult in input order."""
-		params = _cabi.params_from_crop_params(CP, cvrg_window)
+		params = _cabi.params_from_crop_params(CP, cvrg_window, np_int)
 		results = [None] * len(vds)
 		groups = {}
 		for i, vd in enumerate(vds):

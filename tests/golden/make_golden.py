@@ -139,6 +139,10 @@ CLIPS = {
 	# clustering on a 4x down-scaled copy taken with INTER_NEAREST (resize_type 3)
 	'resize_nearest': (dict(seed=2015, fc=120, shot_starts=[50]),
 					dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=4, resize_type=3, select_sum=1), ['3:1']),
+	# the ISM-2021 preset as it behaves on the numpy the reference pins (README.md:85-92, numpy < 1.24): np.int still
+	# exists there, so get_points_on_line (smartVidCrop.py:1377,1384) samples diagonal moves instead of raising into
+	# its own except.  'NPINT' runs the unmodified reference with the alias restored (np.int = int).
+	'best_npint': (dict(seed=2017, fc=220, shot_starts=[120]), 'BEST_NPINT', ['1:3', '3:1']),
 	# a different sampling table: every 3rd frame gets a map, 24 fps
 	'skip3_fr24': (dict(seed=2016, fc=150, fr=24.0, skip=3, shot_starts=[75]), {}, ['9:16']),
 }
@@ -167,7 +171,7 @@ def make_clip_fixtures():
 			vd = _with_empties(vd, None)
 		out = {}
 		out['kw'] = np.array(repr(kw))
-		out['over'] = np.array(repr(over))
+		out['over'] = np.array(repr('BEST' if over == 'BEST_NPINT' else over))
 		out['ratios'] = np.array(ratios)
 		for k in ('smaps', 'segmentation', 'segmentation_sel'):
 			out['in_' + k] = np.asarray(vd[k])
@@ -176,11 +180,20 @@ def make_clip_fixtures():
 		out['in_scalars'] = np.array([vd['fr'], vd['fc'], vd['fc_sel'], vd['h_orig'], vd['w_orig'],
 									vd['h_process'], vd['w_process']], dtype=np.float64)
 		for r in ratios:
-			CP = ref.sc_init_crop_params(use_best_settings=(over == 'BEST'))
-			if over != 'BEST':
+			best = isinstance(over, str) and over.startswith('BEST')
+			npint = isinstance(over, str) and over.endswith('NPINT')
+			CP = ref.sc_init_crop_params(use_best_settings=best)
+			if not best:
 				CP.update(over)
 			CP['out_ratio'] = r
-			VD, res, pre = _capture(vd, CP)
+			if npint:
+				np.int = int      # the alias numpy < 1.24 had; removed again below
+			try:
+				VD, res, pre = _capture(vd, CP)
+			finally:
+				if npint:
+					del np.int
+			out['np_int'] = np.array(1 if npint else 0)
 			tag = r.replace(':', '-')
 			out['bbs_' + tag] = np.array(VD['bbs'], dtype=np.int32)
 			out['dims_' + tag] = np.array([VD['conversion_mode'], VD['w_final'], VD['h_final'],

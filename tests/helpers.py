@@ -8,7 +8,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 CLIP_NAMES = ['c1_default', 'multishot', 'fr25', 'hd1080', 'constant', 'noise', 'few_points',
 			'sumsel_min5', 'noclose_nolp', 'savgol_argmax', 'border', 'empties', 'best_settings', 'best_hd_fr25',
-			'shift_deg1', 'resize_nearest', 'skip3_fr24']
+			'shift_deg1', 'resize_nearest', 'skip3_fr24', 'best_npint']
 
 
 def load_clip_fixture(name):
@@ -29,6 +29,12 @@ def load_clip_fixture(name):
 		over = {k: v for k, v in best.items() if base[k] != v}
 	ratios = [str(r) for r in fx['ratios']]
 	return vd, over, ratios, fx
+
+
+def fixture_np_int(fx):
+	"""True for fixtures generated with numpy's old ``np.int`` alias restored (the behaviour of the numpy the reference
+	pins): the oracle and the library are then run with their np_int switch."""
+	return bool(int(fx['np_int'])) if 'np_int' in fx else False
 
 
 def loess_tolerance(cl):

@@ -6,7 +6,7 @@ import statistics
 import numpy as np
 import pytest
 
-from helpers import CLIP_NAMES, GOLDEN, load_clip_fixture, loess_tolerance
+from helpers import CLIP_NAMES, GOLDEN, fixture_np_int, load_clip_fixture, loess_tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -130,8 +130,12 @@ def test_clip_fixture_end_to_end(engine, name):
 	vd, over, ratios, fx = load_clip_fixture(name)
 	CP = svc.sc_init_crop_params()
 	CP.update(over)
-	res = engine.run([vd], CP, ratios, detail=True, want_filtered=True)[0]
+	res = engine.run([vd], CP, ratios, detail=True, want_filtered=True, np_int=fixture_np_int(fx))[0]
 	assert res.status == 0
+	if CP['focus_stability']:
+		# line-sampling means (smartVidCrop.py:1395-1455) and the centres before the freeze
+		assert _nan_close(res.jumps, fx['jumps'], 0) <= 1e-9
+		assert _nan_close(res.dxnf, fx['dxnf'], 0) <= 1e-9
 	# integer stages: bit-exact
 	filt = np.transpose(res.filtered, (1, 2, 0))
 	assert np.array_equal(filt, fx['smaps_filtered']), 'filtered maps differ in %d maps' % int(

@@ -3,7 +3,7 @@ reference (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from helpers import CLIP_NAMES, load_clip_fixture
+from helpers import CLIP_NAMES, fixture_np_int, load_clip_fixture
 from oracle import sc_oracle
 
 
@@ -24,7 +24,7 @@ def test_oracle_matches_reference_fixture(name):
 		CP = sc_oracle.sc_init_crop_params()
 		CP.update(over)
 		CP['out_ratio'] = r
-		out = sc_oracle.smart_vid_crop_oracle(vd, CP)
+		out = sc_oracle.smart_vid_crop_oracle(vd, CP, np_int=fixture_np_int(fx))
 		tag = r.replace(':', '-')
 		dims = fx['dims_' + tag]
 		assert [out['conversion_mode'], out['w_final'], out['h_final'], out['fbb_w'], out['fbb_h']] == list(dims[:5])
@@ -33,6 +33,10 @@ def test_oracle_matches_reference_fixture(name):
 			# integer stages: bit-exact
 			assert np.array_equal(out['smaps_filtered'], fx['smaps_filtered'])
 			# centroid: sklearn KMeans(1) == unweighted mean to ~1e-13 px
+			if CP['focus_stability']:
+				# the line-sampling means (smartVidCrop.py:1395-1455) and the centres before the freeze
+				_nan_eq(out['jumps'], fx['jumps'], 1e-9)
+				_nan_eq([np.nan if v is None else v for v in out['dxnf']], fx['dxnf'], 1e-9)
 			_nan_eq([np.nan if v is None else v for v in out['dx']], fx['dx'], 1e-9)
 			_nan_eq([np.nan if v is None else v for v in out['dy']], fx['dy'], 1e-9)
 			_nan_eq(out['dxi'], fx['dxi'], 1e-9)
