@@ -430,14 +430,8 @@ def test_focus_stability_sampling_paths(engine):
 		CP = svc.sc_init_crop_params()
 		CP.update(dict(focus_stability=True, com_km=False, min_d_jump=1, foces_stab_t=200, foces_stab_s=3.0, out_ratio='1:3'))
 		want = sc_oracle.smart_vid_crop_oracle(vd, CP, np_int=np_int)
-		engine_params = _cabi.params_from_crop_params(CP, np_int=np_int)
-		# run through the engine with the chosen numpy-compat flag
-		orig = _cabi.params_from_crop_params
-		_cabi.params_from_crop_params = lambda cp, cw='reference', np_int=np_int: orig(cp, cw, np_int)
-		try:
-			res = engine.run([vd], CP, ['1:3'], detail=True)[0]
-		finally:
-			_cabi.params_from_crop_params = orig
+		assert _cabi.params_from_crop_params(CP, np_int=np_int).np_int_compat == int(np_int)
+		res = engine.run([vd], CP, ['1:3'], detail=True, np_int=np_int)[0]
 		assert np.allclose(res.jumps, np.array(want['jumps'], dtype=np.float64), rtol=0, atol=1e-9), np_int
 		assert np.array_equal(res.dx, np.array(want['dx'], dtype=np.float64))
 		assert np.array_equal(res.dxnf, np.array(want['dxnf'], dtype=np.float64))
