@@ -143,6 +143,11 @@ CLIPS = {
 	# exists there, so get_points_on_line (smartVidCrop.py:1377,1384) samples diagonal moves instead of raising into
 	# its own except.  'NPINT' runs the unmodified reference with the alias restored (np.int = int).
 	'best_npint': (dict(seed=2017, fc=220, shot_starts=[120]), 'BEST_NPINT', ['1:3', '3:1']),
+	# oracle-only for now (tests/helpers.py ORACLE_ONLY_NAMES): border detection on a 1080p multi-shot clip, and a 3 s
+	# LOESS window with value_bias / t_threshold / lp_cutoff moved
+	'border_hd_multishot': (dict(seed=2018, fc=260, w_orig=1920, h_orig=1080, shot_starts=[70, 150]), dict(t_border=12), ['3:1', '9:16']),
+	'loess_w3_bias': (dict(seed=2019, fc=320, shot_starts=[200]),
+					dict(loess_w_secs=3, value_bias=0.5, t_threshold=140, lp_cutoff=1.5, hdbscan_min=15), ['4:5']),
 	# a different sampling table: every 3rd frame gets a map, 24 fps
 	'skip3_fr24': (dict(seed=2016, fc=150, fr=24.0, skip=3, shot_starts=[75]), {}, ['9:16']),
 }
@@ -163,6 +168,10 @@ def make_clip_fixtures():
 		specs['empties'] = (dict(seed=2011, fc=240, shot_starts=[100]), {}, ['1:3'])
 	for name, (kw, over, ratios) in specs.items():
 		vd = synth.make_clip(**kw)
+		if name == 'border_hd_multishot':
+			vd['smaps'][:9, :, :] = 0
+			vd['smaps'][-14:, :, :] = 0
+			vd['smaps'][:, :17, :] = 0
 		if name == 'border':
 			# blank borders: zero 12 rows top, 20 cols right in every map
 			vd['smaps'][:12, :, :] = 0

@@ -3,7 +3,7 @@ reference (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from helpers import CLIP_NAMES, fixture_np_int, load_clip_fixture
+from helpers import CLIP_NAMES, ORACLE_ONLY_NAMES, fixture_np_int, load_clip_fixture
 from oracle import sc_oracle
 
 
@@ -17,7 +17,7 @@ def _nan_eq(a, b, tol):
 		assert np.max(np.abs(a[m] - b[m])) <= tol, np.max(np.abs(a[m] - b[m]))
 
 
-@pytest.mark.parametrize('name', CLIP_NAMES)
+@pytest.mark.parametrize('name', CLIP_NAMES + ORACLE_ONLY_NAMES)
 def test_oracle_matches_reference_fixture(name):
 	vd, over, ratios, fx = load_clip_fixture(name)
 	for k, r in enumerate(ratios):
