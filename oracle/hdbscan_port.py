@@ -27,19 +27,25 @@ index ``min_samples`` (self at index 0); scikit-learn takes index
 ``k`` below is the hdbscan convention, i.e. the distance to the k-th nearest
 OTHER point.
 
-Two deliberate, documented choices where the libraries are implementation
-defined (PARITY UNPINNED at this boundary -- the reference holds no golden
-vector for it; pinned here against sklearn on synthetic maps, see
-tests/test_oracle_hdbscan.py):
+Two places where the libraries are implementation defined (PARITY UNPINNED against
+hdbscan==0.8.26 itself -- the reference holds no golden vector for it; PINNED against
+sklearn's port of the same code on synthetic maps: tests/test_oracle_pinned.py,
+tests/golden/hdbscan_fixture.npz):
 
  1. ties between equal edge weights: both libraries use an UNSTABLE
     ``np.argsort``; all coordinates are integer pixels so weights tie massively.
-    The oracle uses a stable sort (ties keep Prim order).
+    The oracle reproduces the permutation of numpy's portable introsort
+    (``numpy_aquicksort`` below, the default ``sort='numpy'`` of
+    ``single_linkage``); the fixtures are generated with numpy's SIMD sorts
+    disabled so that the stand-in library uses the same one
+    (tests/golden/tie_flips.json counts what changes under the SIMD sort).
+    ``sort='stable'`` is kept for experiments only.
  2. stability sums: the libraries accumulate float64 ``(lambda - birth) * size``
     in condensed-tree row order.  The oracle accumulates exactly in 2^-46
     fixed point (lambda_fix(w) = floor(2^46 / w), w an exact integer), which is
     order independent; excess-of-mass decisions can differ from float64 only if
-    two stabilities agree to ~1e-11.
+    two competing stabilities agree to ~1e-11 (tests/test_oracle_pinned.py
+    records the smallest relative gap seen on the fixtures).
 """
 import numpy as np
 
@@ -205,6 +211,10 @@ def single_linkage(order, weight, sort='numpy'):
 	n = len(order)
 	if sort == 'numpy':
 		rows = numpy_aquicksort(weight)
+	elif sort == 'stock':
+		# whatever this machine's numpy does (numpy >= 2.0: an AVX-512 / AVX2 SIMD sort picked at run time); float64 like
+		# the libraries' weight column
+		rows = np.argsort(np.asarray(weight, dtype=np.float64))
 	else:
 		rows = np.argsort(weight, kind='stable')
 	parent = list(range(2 * n - 1))
@@ -299,8 +309,9 @@ def compute_stability(rows, n):
 	return stab
 
 
-def get_clusters(rows, stab, n, allow_single_cluster=True):
-	"""_get_clusters (eom, epsilon 0, no max size) + _do_labelling (_tree.pyx)."""
+def get_clusters(rows, stab, n, allow_single_cluster=True, gaps=None):
+	"""_get_clusters (eom, epsilon 0, no max size) + _do_labelling (_tree.pyx).
+	gaps: optional list that receives (relative gap |children - node| / max, max) of every excess-of-mass comparison."""
 	node_list = sorted(stab.keys(), reverse=True)
 	if not allow_single_cluster:
 		node_list = node_list[:-1]
@@ -312,6 +323,9 @@ def get_clusters(rows, stab, n, allow_single_cluster=True):
 	stab = dict(stab)
 	for node in node_list:
 		sub = sum(stab[c] for c in children.get(node, []))
+		if gaps is not None and children.get(node):
+			# (relative gap, larger of the two sums): a gap of 0 with a sum of 0 is the trivial 0 == 0 of two empty sums
+			gaps.append((abs(sub - stab[node]) / float(max(sub, stab[node], 1)), max(sub, stab[node])))
 		if sub > stab[node]:
 			is_cluster[node] = False
 			stab[node] = sub
@@ -354,7 +368,7 @@ def get_clusters(rows, stab, n, allow_single_cluster=True):
 
 
 def fit_predict(P, min_cluster_size, min_samples=None, allow_single_cluster=True,
-				return_debug=False):
+				return_debug=False, sort='numpy', gaps=None):
 	"""Labels (-1 = noise) for integer points P [n,2] in (row, col) order.
 	Mirrors HDBSCAN(min_cluster_size, min_samples, metric='sqeuclidean',
 	cluster_selection_method='eom', allow_single_cluster=True).fit_predict."""
@@ -366,10 +380,10 @@ def fit_predict(P, min_cluster_size, min_samples=None, allow_single_cluster=True
 		k = 1
 	core = core_distances(P, k)
 	order, weight = prim_order(P, core)
-	hier = single_linkage(order, weight)
+	hier = single_linkage(order, weight, sort=sort)
 	rows = condense_tree(hier, n, min_cluster_size)
 	stab = compute_stability(rows, n)
-	labels = get_clusters(rows, stab, n, allow_single_cluster)
+	labels = get_clusters(rows, stab, n, allow_single_cluster, gaps=gaps)
 	if return_debug:
 		return labels, dict(core=core, order=order, weight=weight, rows=rows, stab=stab)
 	return labels

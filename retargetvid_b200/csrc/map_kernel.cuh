@@ -134,8 +134,8 @@ struct MapArgs {
 };
 
 // split pipeline: point-count classes of the Prim / back launches
-constexpr int kSplitClasses = 5;
-__host__ __device__ constexpr int split_class_cap(int k) { return k == 0 ? 768 : k == 1 ? 1536 : k == 2 ? 2048 : k == 3 ? 3072 : 4096; }
+constexpr int kSplitClasses = 6;
+__host__ __device__ constexpr int split_class_cap(int k) { return k == 0 ? 768 : k == 1 ? 1536 : k == 2 ? 2048 : k == 3 ? 3072 : k == 4 ? 4096 : 8192; }
 constexpr int kModeMono = 0, kModeFront = 1, kModeBack = 2;
 
 __constant__ RingTable c_rings;
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(256) map_stream_kernel(const uint8_t *__restri
 template <int NT, int TPT, int MODE>
 struct MapKernelCfg {
 	// (the monolithic kernel keeps Prim's point registers and the tree code's temporaries alive together: 64 registers)
-	static constexpr int kMinBlocks = (MODE == kModeFront) ? 4 : (NT * TPT <= 1536) ? (MODE == kModeMono ? 4 : 5) : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1;
+	static constexpr int kMinBlocks = (MODE == kModeFront) ? (NT <= 256 ? 4 : 2) : (NT * TPT <= 1536) ? (MODE == kModeMono ? 4 : 5) : (NT * TPT <= 2048) ? 4 : (NT * TPT <= 4096) ? 2 : 1;
 };
 
 // MODE kModeMono: the whole path for one map after the other (cut-adjacent chains, the largest classes, resize).

@@ -18,6 +18,7 @@
 #include "iou_kernel.cuh"
 #include "map_kernel.cuh"
 #include "prim_kernel.cuh"
+#include "fprim_kernel.cuh"
 #include "track_kernels.cuh"
 
 using namespace rvb;
@@ -99,12 +100,13 @@ struct rvb_ctx {
 	int64_t launches = 0;
 	bool phase_on = false;
 	DevBuf phase;
-	bool chain_levels = false;  // RVB_CHAIN_LEVELS=1: chains go through the split pipeline one depth per launch; default: the
-	                            // monolithic kernel walks them on the side stream (measured 6 % faster at 3 batches in flight)
+	bool chain_levels = true;   // cut-adjacent chains go through the split pipeline, one depth per set, on the side stream;
+	                            // RVB_CHAIN_MONO=1: the monolithic kernel walks them instead (the round-1 default)
 	int prim_variant[4] = {0, 0, 0, 0};
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
-	DevBuf scr_pinfo, scr_val, scr_pkey;
+	DevBuf scr_pinfo, scr_val, scr_pkey, scr_far, scr_alist;
+	bool dense_prim = false;   // RVB_DENSE_PRIM=1: the all-pairs prim_kernel instead of the lattice-local fprim_kernel
 	const void *nhw_zero_p = nullptr;   // maps_nhw was cleared at this address for this geometry
 	size_t nhw_zero_cap = 0;
 	int nhw_zero_w = 0, nhw_zero_wps = 0, nhw_zero_h = 0;
@@ -167,6 +169,25 @@ static SmemLayout make_layout(int nmax, int H, int WPS, int W, int mcs, int smal
 	const int map_end = L.map + H * WPS;
 	L.total = align_up(std::max(cluster_end, map_end), 128);
 	return L;
+}
+
+// lattice offsets of the frontier Prim (fprim_kernel.cuh), sorted by squared length, and the weight of each bucket level
+static void build_frontier_table(FrOffsetTable &t) {
+	struct Off { int d2, dy, dx; };
+	std::vector<Off> offs;
+	for (int dy = -5; dy <= 5; ++dy)
+		for (int dx = -5; dx <= 5; ++dx) {
+			const int d2 = dy * dy + dx * dx;
+			if (d2 > 0 && d2 <= kFrR0) offs.push_back({d2, dy, dx});
+		}
+	std::stable_sort(offs.begin(), offs.end(), [](const Off &a, const Off &b) { return a.d2 < b.d2; });
+	memset(&t, 0, sizeof(t));
+	for (int i = 0; i < kFrIters * 32; ++i) {
+		if (i < (int)offs.size()) { t.dy[i] = (int8_t)offs[i].dy; t.dx[i] = (int8_t)offs[i].dx; t.d2[i] = (uint32_t)offs[i].d2; }
+		else { t.dy[i] = 0; t.dx[i] = 0; t.d2[i] = 0x7FFFFFu; }
+	}
+	int l = 0;
+	for (int w = 0; w < 32; ++w) if (kFrLevelMask & (1u << w)) t.level_w[l++] = (uint32_t)w;
 }
 
 static void build_ring_table(RingTable &t) {
@@ -359,14 +380,27 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 		int prio = e ? atoi(e) : 0;
 		prio = std::max(hi, std::min(lo, prio));
 		CU(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio));
-		e = getenv("RVB_CHAIN_LEVELS");
-		c->chain_levels = (e && e[0] == '1');
+		e = getenv("RVB_CHAIN_MONO");
+		c->chain_levels = !(e && e[0] == '1');
 	}
 	CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	RingTable t;
 	build_ring_table(t);
 	CU(cudaMemcpyToSymbol(c_rings, &t, sizeof(t)));
+	{
+		FrOffsetTable ft;
+		build_frontier_table(ft);
+		CU(cudaMemcpyToSymbol(c_froffs, &ft, sizeof(ft)));
+		CU(cudaFuncSetAttribute(fprim_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+		CU(cudaFuncSetAttribute(fprim_kernel<1536>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+		CU(cudaFuncSetAttribute(fprim_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+		CU(cudaFuncSetAttribute(fprim_kernel<3072>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+		CU(cudaFuncSetAttribute(fprim_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+		CU(cudaFuncSetAttribute(fprim_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+		const char *e = getenv("RVB_DENSE_PRIM");
+		c->dense_prim = (e && e[0] == '1');
+	}
 	CU(cudaFuncSetAttribute(map_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -374,6 +408,8 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	CU(cudaFuncSetAttribute(map_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
 	CU(cudaFuncSetAttribute(map_kernel<256, 16, kModeFront>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<512, 8, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 16, kModeFront>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(map_kernel<512, 16, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
 	CU(cudaFuncSetAttribute(prim_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 6, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 8, kModeBack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -398,7 +434,8 @@ extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->maps_in, &c->maps_nhw, &c->filt, &c->meta, &c->mapout, &c->series, &c->scratch,
-					  &c->boxes, &c->misc, &c->iou_a, &c->iou_b, &c->iou_c, &c->scr_pinfo, &c->scr_val, &c->scr_pkey};
+					  &c->boxes, &c->misc, &c->iou_a, &c->iou_b, &c->iou_c, &c->scr_pinfo, &c->scr_val, &c->scr_pkey,
+					  &c->scr_far, &c->scr_alist};
 	for (DevBuf *b : bufs) b->release();
 	c->stage.release();
 	c->stage_out.release();
@@ -503,6 +540,16 @@ static void launch_prim(rvb_ctx *c, const PrimArgs &pa, int n_maps, int smem, cu
 	}
 	const int per_sm = prim_warps_per_sm(KMAX) / NW;
 	prim_kernel<NW, KMAX><<<std::min(n_maps, c->n_sm * per_sm), 32 * NW, smem, stream>>>(pa);
+}
+
+// one frontier-Prim launch: persistent one-warp CTAs, as many per SM as shared memory and registers allow
+template <int CAP>
+static void launch_fprim(rvb_ctx *c, FPrimArgs fa, int n_maps, int H, int W, cudaStream_t stream) {
+	fa.cap = CAP; fa.H = H; fa.W = W; fa.RS = (W + 31) >> 5;
+	const int smem = fprim_smem_bytes(CAP, H, W);
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fprim_kernel<CAP>, 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+	fprim_kernel<CAP><<<std::max(1, std::min(n_maps, c->n_sm * per_sm)), 32, smem, stream>>>(fa);
 }
 
 template <int NT, int TPT, int MODE = kModeMono>
@@ -690,7 +737,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		depth[m] = (pred[m] < 0) ? 0 : depth[m - 1] + 1;   // the predecessor of map m is map m - 1
 		max_depth = std::max(max_depth, depth[m]);
 	}
-	const bool split_chains = split && max_depth < kMaxChainDepth && c->chain_levels;
+	const bool split_chains = split && max_depth < kMaxChainDepth && c->chain_levels && !c->dense_prim;
 	std::vector<int> work;                    // monolithic launches: chain heads (the CTA walks the chain)
 	std::vector<std::vector<int>> sets;       // split pipeline
 	if (split) sets.resize(split_chains ? 2 + max_depth : 1);
@@ -922,6 +969,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				// monolithic launch instead
 				const size_t cap = (size_t)std::min<long long>((long long)n_split * 2048 + 8192, 0x7fffff00LL);
 				if (c->scr_pinfo.ensure(cap * sizeof(uint2)) || c->scr_val.ensure(cap) || c->scr_pkey.ensure(cap * sizeof(uint32_t))) return RVB_ERR_CUDA;
+				if (!c->dense_prim && (c->scr_far.ensure(cap * sizeof(uint32_t)) || c->scr_alist.ensure(cap * sizeof(uint32_t)))) return RVB_ERR_CUDA;
 				a.scr_off = (int *)(M + o_scroff); a.scr_top = (unsigned long long *)(cnt + cnt_scr); a.scr_cap = (unsigned int)cap;
 				a.scr_pinfo = (uint2 *)c->scr_pinfo.p; a.scr_val = (uint8_t *)c->scr_val.p; a.scr_pkey = (uint32_t *)c->scr_pkey.p;
 				a.skip = M + o_skip;
@@ -929,18 +977,38 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				memset(&pa, 0, sizeof(pa));
 				pa.out = (const MapOut *)c->mapout.p; pa.scr_off = a.scr_off; pa.scr_pinfo = a.scr_pinfo; pa.scr_pkey = a.scr_pkey;
 				pa.phase_cycles = a.phase_cycles;
+				FPrimArgs fa;
+				memset(&fa, 0, sizeof(fa));
+				fa.out = pa.out; fa.scr_off = pa.scr_off; fa.scr_pinfo = pa.scr_pinfo; fa.scr_pkey = pa.scr_pkey;
+				fa.scr_far = (uint32_t *)c->scr_far.p; fa.scr_alist = (uint32_t *)c->scr_alist.p;
+				fa.phase_cycles = a.phase_cycles;
+				fa.work = a.phase_cycles ? a.phase_cycles + 12 : nullptr;
 				// front: load .. core distances.  Its overflow (more than 4096 points, or scratch full) lands in the list
 				// of the monolithic class of 8192 points, which also walks the rest of that map's chain.
 				auto launch_front = [&](int set, cudaStream_t stream) -> int {
 					const int ns = (int)sets[set].size();
 					if (ns == 0) return RVB_OK;
 					int *sc = cnt + 10 + set * kSetCounters;
-					a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
 					a.cls_lists = (int *)(M + o_cls) + (size_t)kSplitClasses * set_list_off[set]; a.cls_cnt = sc + 2; a.cls_stride = ns;
+					a.force_class = -1;
+					int rc = RVB_OK;
+					if (set == 0) {
+						// the bulk of the maps: 4096-point front CTAs (4 per SM); a larger map is handed to the wide front below
+						a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
+						const bool wide = !c->dense_prim;   // (the all-pairs prim_kernel stops at 4096 points)
+						a.ovf_list = wide ? ovf[0] : ovf[3]; a.ovf_len = wide ? cnt + 2 * 1 + 1 : cnt + 2 * 4 + 1;
+						rc = launch_map<256, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 16, kModeFront>(c, make_layout(4096, H, WPS, W, mcs, 0, true).total, ns), stream);
+						if (rc || !wide) return rc;
+						a.list = ovf[0]; a.head = cnt + 2 * 1; a.list_len = cnt + 2 * 1 + 1;
+					} else {
+						// a chain set: few maps, made larger by the blend
+						a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
+					}
+					// wide front (8192 points).  What it cannot place (more points than that -> flagged by the monolithic
+					// launch, or scratch exhausted) goes to the monolithic class of 8192 points, which also walks the rest
+					// of that map's chain.
 					a.ovf_list = ovf[3]; a.ovf_len = cnt + 2 * 4 + 1;
-					// a chain set has few maps and the next depth waits for it: one launch with the widest shape per stage
-					a.force_class = (set > 0) ? kSplitClasses - 1 : -1;
-					return launch_map<256, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 16, kModeFront>(c, make_layout(4096, H, WPS, W, mcs, 0, true).total, ns), stream);
+					return launch_map<512, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<512, 16, kModeFront>(c, make_layout(8192, H, WPS, W, mcs, 0, true).total, set == 0 ? std::min(ns, c->n_sm) : ns), stream);
 				};
 				// Prim and back, one launch each per size class
 				auto launch_prim_back = [&](int set, cudaStream_t stream) -> int {
@@ -948,14 +1016,23 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 					if (ns == 0) return RVB_OK;
 					int *sc = cnt + 10 + set * kSetCounters;
 					int *lists = (int *)(M + o_cls) + (size_t)kSplitClasses * set_list_off[set];
-					const int k_first = (set > 0) ? kSplitClasses - 1 : 0;
+					const int k_first = 0;
 					for (int k = k_first; k < kSplitClasses; ++k) {
 						pa.list = lists + (size_t)k * ns; pa.list_len = sc + 2 + k; pa.head = sc + 2 + kSplitClasses + k;
 						pa.cap = split_class_cap(k);
 						const int smem = 12 * pa.cap;
 						// (warps per map, register slots per thread): 16 warps per SM in every class -- a warp issues at most
 						// every third cycle in this loop (half-rate integer pipe + dependent latency)
-						const int v = c->prim_variant[k];
+						const int v = c->dense_prim ? (k < 4 ? c->prim_variant[k] : 0) : -1;
+						if (v < 0) {
+							fa.list = pa.list; fa.list_len = pa.list_len; fa.head = pa.head;
+							if (k == 0) launch_fprim<768>(c, fa, ns, H, W, stream);
+							if (k == 1) launch_fprim<1536>(c, fa, ns, H, W, stream);
+							if (k == 2) launch_fprim<2048>(c, fa, ns, H, W, stream);
+							if (k == 3) launch_fprim<3072>(c, fa, ns, H, W, stream);
+							if (k == 4) launch_fprim<4096>(c, fa, ns, H, W, stream);
+							if (k == 5) launch_fprim<8192>(c, fa, ns, H, W, stream);
+						}
 						if (k == 0 && v == 0) launch_prim<1, 24>(c, pa, ns, smem, stream);
 						if (k == 0 && v == 1) launch_prim<2, 12>(c, pa, ns, smem, stream);
 						if (k == 1 && v == 0) launch_prim<2, 24>(c, pa, ns, smem, stream);
@@ -964,7 +1041,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 						if (k == 2 && v == 1) launch_prim<4, 16>(c, pa, ns, smem, stream);
 						if (k == 3 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
 						if (k == 3 && v == 1) launch_prim<8, 12>(c, pa, ns, smem, stream);
-						if (k == 4) launch_prim<8, 16>(c, pa, ns, smem, stream);
+						if (k >= 4 && v >= 0) launch_prim<8, 16>(c, pa, ns, smem, stream);
 						CU(cudaGetLastError());
 						c->launches += 1;
 						c->map_launches += 1;
@@ -978,6 +1055,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 						if (k == 2) rc = launch_map<256, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 8, kModeBack>(c, make_layout(2048, H, WPS, W, mcs, 0).total, ns), stream);
 						if (k == 3) rc = launch_map<512, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 6, kModeBack>(c, make_layout(3072, H, WPS, W, mcs, 0).total, ns), stream);
 						if (k == 4) rc = launch_map<512, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 8, kModeBack>(c, make_layout(4096, H, WPS, W, mcs, 0).total, ns), stream);
+						if (k == 5) rc = launch_map<512, 16, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 16, kModeBack>(c, make_layout(8192, H, WPS, W, mcs, 0).total, ns), stream);
 						if (rc) return rc;
 					}
 					return RVB_OK;

@@ -4,10 +4,11 @@ into one ``rvb_crop_track_batch`` call per process size and unpacks the results.
 Host logic only (dict plumbing); all arithmetic runs in the CUDA library.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
-from . import _cabi
+from . import _cabi, sharding
 
 
 def parse_ratio(out_ratio):
@@ -35,6 +36,9 @@ class CropEngine(object):
 		"""vds: list of vid_data dicts; ratios: list of 'a:b' strings.
 		np_int: focus stability samples diagonal moves as the reference does on the numpy it pins (np.int exists,
 		smartVidCrop.py:1377,1384) instead of returning 255 for them as it does on numpy >= 1.24.
+		raise_on_clip_error=False: a clip that fails on its own (RVB_ERR_CAPACITY: a map with more salient pixels than
+		RVB_MAX_POINTS; RVB_ERR_NO_CENTRES: no salient pixel at all) is reported through ClipResult.status and the
+		other clips of the batch keep their results.
 		Returns a list of ClipResult in input order."""
 		params = _cabi.params_from_crop_params(CP, cvrg_window, np_int)
 		results = [None] * len(vds)
@@ -160,3 +164,52 @@ class CropEngine(object):
 			results[idxs[i]] = res
 		del keep
 		return err
+
+
+class MultiGpuCropEngine(object):
+	"""Per-video sharding over the GPUs of one box: replaces the serial loop over videos of the
+	reference's driver (smartVidCrop.py:2722-2726).  One CropEngine (context, stream, workspace) and one host thread per
+	device, videos assigned longest-processing-time-first by their number of saliency maps, all target ratios of a video
+	on the same device, results gathered on the host in input order.  No collective: videos never interact."""
+
+	def __init__(self, devices):
+		devices = [int(d) for d in devices]
+		if not devices or len(set(devices)) != len(devices):
+			raise ValueError('devices must be a non-empty list of distinct CUDA device indices')
+		self.devices = devices
+		self.engines = [CropEngine(d) for d in devices]
+
+	def close(self):
+		for e in self.engines:
+			e.close()
+
+	def shards(self, vds):
+		return sharding.lpt_shards([int(vd['fc_sel']) for vd in vds], len(self.engines))
+
+	def run(self, vds, CP, ratios, **kw):
+		"""Same arguments and result as CropEngine.run."""
+		shards = self.shards(vds)
+		parts = [None] * len(self.engines)
+		errs = [None] * len(self.engines)
+
+		def work(k):
+			try:
+				if shards[k]:
+					parts[k] = self.engines[k].run([vds[i] for i in shards[k]], CP, ratios, **kw)
+				else:
+					parts[k] = []
+			except BaseException as e:      # re-raised on the calling thread
+				errs[k] = e
+		ths = [threading.Thread(target=work, args=(k,)) for k in range(len(self.engines))]
+		for t in ths:
+			t.start()
+		for t in ths:
+			t.join()
+		for e in errs:
+			if e is not None:
+				raise e
+		out = [None] * len(vds)
+		for k, idxs in enumerate(shards):
+			for i, r in zip(idxs, parts[k]):
+				out[i] = r
+		return out

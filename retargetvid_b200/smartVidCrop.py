@@ -18,7 +18,7 @@ import time
 import numpy as np
 
 from . import _cabi
-from .engine import CropEngine
+from .engine import CropEngine, MultiGpuCropEngine
 
 _ENGINES = {}
 
@@ -27,6 +27,19 @@ def _engine(device=0):
 	if device not in _ENGINES:
 		_ENGINES[device] = CropEngine(device)
 	return _ENGINES[device]
+
+
+def _multi_engine(devices):
+	key = tuple(int(d) for d in devices)
+	if key not in _ENGINES:
+		_ENGINES[key] = MultiGpuCropEngine(key)
+	return _ENGINES[key]
+
+
+def _pick_engine(device, devices):
+	if devices is not None and len(devices) > 1:
+		return _multi_engine(devices)
+	return _engine(device if not devices else int(devices[0]))
 
 
 # Initiates the SmartVidCrop method's parameters to the default settings
@@ -165,22 +178,65 @@ def _fill_vd(VD, CP, res, ratio_index, want_smaps):
 	return VD
 
 
+def _pad_decision(CP, res, ratio_index):
+	"""The two exits of smart_vid_crop that replace smart-cropping by padding (smartVidCrop.py:2310-2320, :2380-2395),
+	with the decisions of SURVEY.md Appendix B-2 / B-3."""
+	do_pad = False
+	if CP['exit_on_spread_sal'] and res.mean_sal_score > CP['t_sal']:
+		do_pad = True   # Appendix B-3: compare mean_sal_score (the reference reads an unset key)
+	if CP['exit_on_low_cvrg'] and float(res.cvrg_scores[ratio_index]) < CP['t_cvrg']:
+		do_pad = True
+	return do_pad
+
+
+def _results_dict(VD, CP, do_pad, t_dict):
+	"""smart_crop_results with the reference's keys in the reference's order (smartVidCrop.py:2374,2544,2552,2581-2610)."""
+	r = {}
+	r['cuts_clust'] = 0
+	r['result'] = 'padded' if do_pad else 'smart cropped'
+	r['info'] = ' (%dx%d)->(%dx%d)->(%dx%d)->(%dx%d)\n' % \
+		(VD['h_orig'], VD['w_orig'], VD['h_process'], VD['w_process'],
+		VD['h_final'], VD['w_final'], VD['fbb_h'], VD['fbb_w'])
+	params_string = ''
+	for cpk in CP.keys():
+		params_string += ' %-18s : %s\n' % (cpk, str(CP[cpk]))
+	r['params'] = params_string
+	r['mean_sal_score'] = VD['mean_sal_score']
+	r['mean_sal_score_t'] = CP['t_sal']
+	r['coverage_score'] = VD['mean_cvrg_score']
+	r['coverage_score_t'] = CP['t_cvrg']
+	for k in t_dict.keys():
+		if k.startswith('_'):
+			r['t_' + k] = t_dict[k]
+	for k in t_dict.keys():
+		if not k.startswith('_'):
+			r['t_' + k] = t_dict[k]
+	return r
+
+
+_PAD_DROPS = ('bbs', 'dx', 'dy', 'dxnf', 'dynf', 'dxi', 'dyi', 'dxl', 'dyl', 'dxs', 'dys', 'ts')
+
+
 def smart_vid_crop_batch(vid_datas, CP=None, out_ratios=None, device=0, detail=True, want_filtered=False,
-						cvrg_window='reference'):
+						cvrg_window='reference', devices=None, raise_on_clip_error=False):
 	"""Batched entry point: many videos x many target ratios in one pass.
 
 	vid_datas: list of vid_data dicts (ingest output, smartVidCrop.py:480-489).
 	out_ratios: list of 'a:b' strings (default [CP['out_ratio']]).
-	Returns a list (per video) of engine.ClipResult; boxes[r] is the [fc, 4]
-	int32 array of x1,y1,x2,y2 for out_ratios[r].
+	devices: list of CUDA device indices: the videos are sharded per video over these GPUs (one context and host thread
+	per device, longest first by map count, results gathered on the host in input order) -- the serial loop over videos
+	of the reference's driver (smartVidCrop.py:2722-2726) run in parallel.  Default: the single `device`.
+	Returns a list (per video) of engine.ClipResult; boxes[r] is the [fc, 4] int32 array of x1,y1,x2,y2 for
+	out_ratios[r].  A video that fails on its own (ClipResult.status != 0: more salient pixels in a map than
+	RVB_MAX_POINTS, or no salient pixel at all) does not take the others down unless raise_on_clip_error is set.
 	"""
 	if CP is None:
 		CP = sc_init_crop_params()
 	_check_supported(CP)
 	if out_ratios is None:
 		out_ratios = [CP['out_ratio']]
-	return _engine(device).run(vid_datas, CP, list(out_ratios), detail=detail, want_filtered=want_filtered,
-								cvrg_window=cvrg_window)
+	return _pick_engine(device, devices).run(vid_datas, CP, list(out_ratios), detail=detail, want_filtered=want_filtered,
+											cvrg_window=cvrg_window, raise_on_clip_error=raise_on_clip_error)
 
 
 def smart_vid_crop(video_path, CP=None,
@@ -196,7 +252,10 @@ def smart_vid_crop(video_path, CP=None,
 	if CP is None:
 		CP = sc_init_crop_params()
 	_check_supported(CP)
-	if save_vid:
+	if save_vid and (final_vid_fn or demo_fn or plots_fn or frames_dir):
+		# rendering (sc_renderer / sc_render_padded, smartVidCrop.py:1801-2213) is out of scope: asking for an output
+		# video is an error; the reference's default save_vid=True with no output file name set has nothing to write
+		# and runs the crop selection only
 		raise NotImplementedError('rendering (sc_renderer / sc_render_padded) is out of scope; call with save_vid=False')
 
 	VD = vid_data
@@ -237,40 +296,15 @@ def smart_vid_crop(video_path, CP=None,
 	if res.status != _cabi.RVB_OK:
 		raise _cabi.RvbError(res.status, 'a saliency map has more than %d salient pixels' % _cabi.RVB_MAX_POINTS)
 
-	do_pad = False
-	if CP['exit_on_spread_sal'] and res.mean_sal_score > CP['t_sal']:
-		do_pad = True   # Appendix B-3: compare mean_sal_score (the reference reads an unset key)
-	if CP['exit_on_low_cvrg'] and float(res.cvrg_scores[0]) < CP['t_cvrg']:
-		do_pad = True
+	do_pad = _pad_decision(CP, res, 0)
 	VD = _fill_vd(VD, CP, res, 0, want_smaps=True)
-	smart_crop_results['cuts_clust'] = 0
 	if do_pad:
 		# Appendix B-2: the reference's pad path raises KeyError('dx'); return the state its
 		# caller anticipates ("Bounding boxes are not available", smartVidCrop.py:2788-2790)
-		for k in ('bbs', 'dx', 'dy', 'dxnf', 'dynf', 'dxi', 'dyi', 'dxl', 'dyl', 'dxs', 'dys', 'ts'):
+		for k in _PAD_DROPS:
 			VD.pop(k, None)
-		smart_crop_results['result'] = 'padded'
-	else:
-		smart_crop_results['result'] = 'smart cropped'
-
-	smart_crop_results['info'] = ' (%dx%d)->(%dx%d)->(%dx%d)->(%dx%d)\n' % \
-		(VD['h_orig'], VD['w_orig'], VD['h_process'], VD['w_process'],
-		VD['h_final'], VD['w_final'], VD['fbb_h'], VD['fbb_w'])
-	params_string = ''
-	for cpk in CP.keys():
-		params_string += ' %-18s : %s\n' % (cpk, str(CP[cpk]))
-	smart_crop_results['params'] = params_string
-	smart_crop_results['mean_sal_score'] = VD['mean_sal_score']
-	smart_crop_results['mean_sal_score_t'] = CP['t_sal']
-	smart_crop_results['coverage_score'] = VD['mean_cvrg_score']
-	smart_crop_results['coverage_score_t'] = CP['t_cvrg']
 	t_dict = _times_dict(VD['fc'] / VD['fr'], t_map, t_total, ingest_times)
-	for k in t_dict.keys():
-		if k.startswith('_'):
-			smart_crop_results['t_' + k] = t_dict[k]
-	for k in t_dict.keys():
-		if not k.startswith('_'):
-			smart_crop_results['t_' + k] = t_dict[k]
+	smart_crop_results.update(_results_dict(VD, CP, do_pad, t_dict))
 	if verbose:
 		print(' Times::')
 		for k, v in t_dict.items():
@@ -287,16 +321,18 @@ def write_result_files(results_out, suffix, vid_data, info_dict):
 	with open(os.path.join(results_out, suffix + '_info.txt'), 'w') as stfp:
 		for k in info_dict.keys():
 			stfp.write(k + ':' + str(info_dict[k]) + '\n')
+	if 'bbs' not in vid_data:
+		return      # padded: "Bounding boxes are not available" (smartVidCrop.py:2788-2790)
 	with open(os.path.join(results_out, suffix + '.txt'), 'w') as bbfp:
-		for bb in vid_data['bbs']:
-			bbfp.write('%d,%d,%d,%d\n' % (bb[0], bb[1], bb[2], bb[3]))
+		bbfp.write(''.join(['%d,%d,%d,%d\n' % (bb[0], bb[1], bb[2], bb[3]) for bb in vid_data['bbs']]))
 
 
 def process_pickles(pickle_paths, results_out_top, aspect_ratios_to_test=('1:3', '3:1'), crop_params=None,
-					test_name='default_config', device=0):
+					test_name='default_config', device=0, devices=None, cvrg_window='reference'):
 	"""The reference's batch driver (smartVidCrop.py:2722-2785) over ingest pickles: for every
-	(aspect ratio, video) writes results/<test_name>/<vid>_<a>-<b>.txt and _info.txt.  All
-	ratios of a video are evaluated from one GPU pass."""
+	(aspect ratio, video) writes results/<test_name>/<vid>_<a>-<b>.txt and _info.txt with the keys and the padding
+	decisions of smart_vid_crop.  All ratios of a video are evaluated from one GPU pass; devices=[...] shards the
+	videos over several GPUs.  Returns the per-video ClipResults (status != 0: that video failed, nothing written)."""
 	CP = sc_init_crop_params() if crop_params is None else dict(crop_params)
 	_check_supported(CP)
 	vds = []
@@ -306,23 +342,25 @@ def process_pickles(pickle_paths, results_out_top, aspect_ratios_to_test=('1:3',
 			vds.append(pickle.load(fp))
 		names.append(os.path.basename(pth).split('.')[0])
 	t0 = time.perf_counter()
-	eng = _engine(device)
-	results = eng.run(vds, CP, list(aspect_ratios_to_test), detail=True)
+	eng = _pick_engine(device, devices)
+	results = eng.run(vds, CP, list(aspect_ratios_to_test), detail=True, cvrg_window=cvrg_window, raise_on_clip_error=False)
 	t_total = time.perf_counter() - t0
-	t_map = eng.ctx.last_map_kernel_ms()[0] / 1000.0
+	t_map = eng.ctx.last_map_kernel_ms()[0] / 1000.0 if hasattr(eng, 'ctx') else 0.0
 	results_out = os.path.join(results_out_top, str(test_name))
 	for vd, name, res in zip(vds, names, results):
+		if res.status != _cabi.RVB_OK:
+			# this video failed on its own (the reference would have raised inside its loop); the others are written
+			continue
 		share = float(vd['fc_sel']) / float(sum(v['fc_sel'] for v in vds))
 		for r, orp in enumerate(aspect_ratios_to_test):
 			cp = dict(CP)
 			cp['out_ratio'] = orp
+			do_pad = _pad_decision(cp, res, r)
 			VD = _fill_vd(dict(vd), cp, res, r, want_smaps=False)
-			info = {'cuts_clust': 0, 'result': 'smart cropped'}
-			info['info'] = ' (%dx%d)->(%dx%d)->(%dx%d)->(%dx%d)\n' % (VD['h_orig'], VD['w_orig'], VD['h_process'],
-																	VD['w_process'], VD['h_final'], VD['w_final'],
-																	VD['fbb_h'], VD['fbb_w'])
 			t_dict = _times_dict(VD['fc'] / VD['fr'], t_map * share, t_total * share, dict(vd.get('times', {})))
-			for k, v in t_dict.items():
-				info['t_' + k] = v
+			info = _results_dict(VD, cp, do_pad, t_dict)
+			if do_pad:
+				for k in _PAD_DROPS:
+					VD.pop(k, None)
 			write_result_files(results_out, name + '_' + str(orp.replace(':', '-')), VD, info)
 	return results
