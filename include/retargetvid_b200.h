@@ -136,6 +136,11 @@ typedef struct rvb_iou_batch {
 	const int32_t *annot_boxes;   /* [n_users][sum F][4] */
 	double   *frame_iou;          /* optional [n_users][sum F] */
 	uint64_t *acc;                /* [n_videos][n_users][2]: exact sum of the IoU doubles in units of 2^-80, lo then hi */
+	const int32_t *n_eval_user;   /* optional HOST [n_videos][n_users]: frames evaluated per (video, annotator); overrides n_eval
+	                                 (the reference breaks out of the frame loop per annotator, retargetvid_eval.py:163-179) */
+	int32_t  *n_bad;              /* optional [1]: IoUs outside [0, 1] (malformed boxes: x2 < x1, empty union).  The reference
+	                                 averages such negative values or raises ZeroDivisionError (retargetvid_eval.py:24-26);
+	                                 with host buffers the call returns RVB_ERR_INVALID when the count is not 0 */
 } rvb_iou_batch;
 
 const char *rvb_version(void);
@@ -152,7 +157,8 @@ int64_t rvb_ctx_launch_count(const rvb_ctx *ctx);
  * kernel) summed over the last crop_track call; valid after a synchronise */
 int rvb_ctx_last_map_kernel_ms(rvb_ctx *ctx, float *ms, int32_t *launches);
 /* split pipeline of the last crop_track call, CUDA-event times (ms) on the launching stream:
- * out = {front launch, Prim launches, back launches, whole map pipeline incl. the joined side stream} */
+ * out = {front launches, Prim + back launches of the maps outside cut-adjacent chains (the size classes run side by
+ * side on their own streams), 0, whole map pipeline incl. the joined side stream with the chains} */
 int rvb_ctx_last_stage_ms(rvb_ctx *ctx, float out[4]);
 
 /* profiling aid: when enabled, the map kernel accumulates SM cycles per phase (11 phases: load, threshold+compact,

@@ -74,7 +74,7 @@ class rvb_batch(C.Structure):
 class rvb_iou_batch(C.Structure):
 	_fields_ = [('n_videos', C.c_int32), ('n_users', C.c_int32), ('mem_space', C.c_int32), ('reserved0', C.c_int32),
 				('frame_offset', C.c_void_p), ('n_eval', C.c_void_p), ('method_boxes', C.c_void_p),
-				('annot_boxes', C.c_void_p), ('frame_iou', C.c_void_p), ('acc', C.c_void_p)]
+				('annot_boxes', C.c_void_p), ('frame_iou', C.c_void_p), ('acc', C.c_void_p), ('n_eval_user', C.c_void_p), ('n_bad', C.c_void_p)]
 
 
 _lib = None
@@ -120,7 +120,8 @@ def check(code):
 def params_from_crop_params(CP, cvrg_window='reference', np_int=False):
 	"""crop_params dict (sc_init_crop_params keys) -> rvb_params."""
 	p = rvb_params()
-	p.t_threshold = int(CP['t_threshold'])
+	# `smaps < t` on uint8 values with a fractional t keeps exactly the values >= ceil(t) (smartVidCrop.py:1057)
+	p.t_threshold = int(-(-float(CP['t_threshold']) // 1))
 	p.clust_filt = 1 if CP['clust_filt'] else 0
 	p.hdbscan_min = int(CP['hdbscan_min'])
 	p.hdbscan_min_samples = 0 if CP['hdbscan_min_samples'] is None else int(CP['hdbscan_min_samples'])

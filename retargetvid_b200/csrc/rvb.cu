@@ -88,7 +88,11 @@ struct rvb_ctx {
 	int device = 0;
 	int n_sm = 0;
 	cudaStream_t own_stream = nullptr;
-	cudaStream_t side_stream = nullptr;   // monolithic launches (chains) run beside the split pipeline
+	cudaStream_t side_stream = nullptr;   // cut-adjacent chains (and monolithic fallbacks) run beside the main set
+	cudaStream_t cls_stream[kSplitClasses] = {};   // one per size class: Prim + back of the classes run side by side
+	cudaEvent_t ev_cls[kSplitClasses] = {};
+	cudaEvent_t ev_cls_fork = nullptr;
+	bool serial_classes = false;          // RVB_SERIAL_CLASSES=1: the classes one after the other on the main stream
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_map0 = nullptr, ev_map1 = nullptr, ev_stage = nullptr;
@@ -106,7 +110,8 @@ struct rvb_ctx {
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
 	DevBuf scr_pinfo, scr_val, scr_pkey, scr_far, scr_alist;
-	bool dense_prim = false;   // RVB_DENSE_PRIM=1: the all-pairs prim_kernel instead of the lattice-local fprim_kernel
+	bool dense_prim = true;    // the all-pairs prim_kernel (default, the faster one as measured: DESIGN.md 4.1);
+	                           // RVB_FRONTIER_PRIM=1: the lattice-local fprim_kernel (exact too, kept for the record)
 	const void *nhw_zero_p = nullptr;   // maps_nhw was cleared at this address for this geometry
 	size_t nhw_zero_cap = 0;
 	int nhw_zero_w = 0, nhw_zero_wps = 0, nhw_zero_h = 0;
@@ -183,8 +188,8 @@ static void build_frontier_table(FrOffsetTable &t) {
 	std::stable_sort(offs.begin(), offs.end(), [](const Off &a, const Off &b) { return a.d2 < b.d2; });
 	memset(&t, 0, sizeof(t));
 	for (int i = 0; i < kFrIters * 32; ++i) {
-		if (i < (int)offs.size()) { t.dy[i] = (int8_t)offs[i].dy; t.dx[i] = (int8_t)offs[i].dx; t.d2[i] = (uint32_t)offs[i].d2; }
-		else { t.dy[i] = 0; t.dx[i] = 0; t.d2[i] = 0x7FFFFFu; }
+		if (i < (int)offs.size()) { t.dy[i] = (int8_t)offs[i].dy; t.dx[i] = (int8_t)offs[i].dx; t.lev[i] = (uint8_t)fr_level_of((uint32_t)offs[i].d2); }
+		else { t.dy[i] = 0; t.dx[i] = 0; t.lev[i] = (uint8_t)kFrLevInf; }
 	}
 	int l = 0;
 	for (int w = 0; w < 32; ++w) if (kFrLevelMask & (1u << w)) t.level_w[l++] = (uint32_t)w;
@@ -383,6 +388,15 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 		e = getenv("RVB_CHAIN_MONO");
 		c->chain_levels = !(e && e[0] == '1');
 	}
+	for (int k = 0; k < kSplitClasses; ++k) {
+		CU(cudaStreamCreateWithFlags(&c->cls_stream[k], cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&c->ev_cls[k], cudaEventDisableTiming));
+	}
+	CU(cudaEventCreateWithFlags(&c->ev_cls_fork, cudaEventDisableTiming));
+	{
+		const char *e = getenv("RVB_SERIAL_CLASSES");
+		c->serial_classes = (e && e[0] == '1');
+	}
 	CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	RingTable t;
@@ -392,14 +406,14 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 		FrOffsetTable ft;
 		build_frontier_table(ft);
 		CU(cudaMemcpyToSymbol(c_froffs, &ft, sizeof(ft)));
-		CU(cudaFuncSetAttribute(fprim_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-		CU(cudaFuncSetAttribute(fprim_kernel<1536>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-		CU(cudaFuncSetAttribute(fprim_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-		CU(cudaFuncSetAttribute(fprim_kernel<3072>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-		CU(cudaFuncSetAttribute(fprim_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-		CU(cudaFuncSetAttribute(fprim_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-		const char *e = getenv("RVB_DENSE_PRIM");
-		c->dense_prim = (e && e[0] == '1');
+		CU(cudaFuncSetAttribute(fprim_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		CU(cudaFuncSetAttribute(fprim_kernel<1536>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		CU(cudaFuncSetAttribute(fprim_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		CU(cudaFuncSetAttribute(fprim_kernel<3072>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		CU(cudaFuncSetAttribute(fprim_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		CU(cudaFuncSetAttribute(fprim_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		const char *e = getenv("RVB_FRONTIER_PRIM");
+		c->dense_prim = !(e && e[0] == '1');
 	}
 	CU(cudaFuncSetAttribute(map_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	CU(cudaFuncSetAttribute(map_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -446,6 +460,11 @@ extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->ev_join) cudaEventDestroy(c->ev_join);
 	if (c->side_stream) cudaStreamDestroy(c->side_stream);
+	for (int k = 0; k < kSplitClasses; ++k) {
+		if (c->ev_cls[k]) cudaEventDestroy(c->ev_cls[k]);
+		if (c->cls_stream[k]) cudaStreamDestroy(c->cls_stream[k]);
+	}
+	if (c->ev_cls_fork) cudaEventDestroy(c->ev_cls_fork);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return RVB_OK;
@@ -620,6 +639,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	if (H < 1 || W < 1 || H > 256 || W > 256) return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d (max 256x256)", H, W);
 	if (p->hdbscan_min < 2) return fail(RVB_ERR_INVALID, "hdbscan_min=%d (min_cluster_size must be >= 2)", p->hdbscan_min);
 	if (p->loess_degree < 1 || p->loess_degree > 2) return fail(RVB_ERR_UNSUPPORTED, "loess_degree=%d", p->loess_degree);
+	if (p->lp_filt && p->lp_order > RVB_MAX_LP_ORDER)
+		return fail(RVB_ERR_UNSUPPORTED, "lp_order=%d (scipy designs any order; this build stops at %d)", p->lp_order, RVB_MAX_LP_ORDER);
 	if (!b->clips || !b->shots || !b->true_inds || (!b->maps && !b->clip_maps) || !b->boxes) return fail(RVB_ERR_INVALID, "NULL array in batch");
 	if (p->t_border != -1 && b->maps_kind == RVB_MAPS_F32_NHW)
 		return fail(RVB_ERR_UNSUPPORTED, "border detection on float32 maps is not built");
@@ -757,7 +778,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	// counters: [0..9] per monolithic capacity class {head, len} of that class's work list; then per split set
 	// kSetCounters ints: {front head, front len, class lengths[5], Prim heads[5], back heads[5]}; then the scratch
 	// allocator (64 bit)
-	constexpr int kSetCounters = 2 + 3 * kSplitClasses + 1;
+	constexpr int kSetCounters = 2 + 3 * kSplitClasses + 3;   // ... + {wide-front head, len} + pad
 	const int cnt_scr = (10 + n_sets * kSetCounters + 1) & ~1;
 	std::vector<int> counters(cnt_scr + 2, 0);
 	counters[1] = (int)work.size();
@@ -794,6 +815,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf3 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf4 = sg.add(nullptr, (size_t)NM * sizeof(int));
+	const size_t o_ovfw = sg.add(nullptr, (size_t)NM * sizeof(int));   // maps the 4096-point front hands to the wide front
 	const size_t o_work2 = sg.add(split_all.data(), split_all.size() * sizeof(int));
 	const size_t o_cls = sg.add(nullptr, (size_t)kSplitClasses * n_split * sizeof(int));
 	const size_t o_scroff = sg.add(nullptr, (size_t)(split ? NM : 0) * sizeof(int));
@@ -806,6 +828,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_mscore = sg.add(nullptr, (size_t)NM * sizeof(double));
 	const size_t o_minfo = sg.add(nullptr, (size_t)NM * 4 * sizeof(int));
 	const size_t o_empty = sg.add(nullptr, (size_t)NM);
+	const size_t o_minmax = sg.add(nullptr, (size_t)NS * 4 * sizeof(double));
 	const size_t meta_bytes = sg.bytes.size();
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
 	if (c->stage.ensure(meta_bytes)) return RVB_ERR_CUDA;
@@ -982,7 +1005,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				fa.out = pa.out; fa.scr_off = pa.scr_off; fa.scr_pinfo = pa.scr_pinfo; fa.scr_pkey = pa.scr_pkey;
 				fa.scr_far = (uint32_t *)c->scr_far.p; fa.scr_alist = (uint32_t *)c->scr_alist.p;
 				fa.phase_cycles = a.phase_cycles;
-				fa.work = a.phase_cycles ? a.phase_cycles + 12 : nullptr;
+				fa.work = a.phase_cycles ? a.phase_cycles + 11 : nullptr;
 				// front: load .. core distances.  Its overflow (more than 4096 points, or scratch full) lands in the list
 				// of the monolithic class of 8192 points, which also walks the rest of that map's chain.
 				auto launch_front = [&](int set, cudaStream_t stream) -> int {
@@ -996,10 +1019,11 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 						// the bulk of the maps: 4096-point front CTAs (4 per SM); a larger map is handed to the wide front below
 						a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
 						const bool wide = !c->dense_prim;   // (the all-pairs prim_kernel stops at 4096 points)
-						a.ovf_list = wide ? ovf[0] : ovf[3]; a.ovf_len = wide ? cnt + 2 * 1 + 1 : cnt + 2 * 4 + 1;
+						int *ovfw = (int *)(M + o_ovfw);
+						a.ovf_list = wide ? ovfw : ovf[3]; a.ovf_len = wide ? sc + 2 + 3 * kSplitClasses + 1 : cnt + 2 * 4 + 1;
 						rc = launch_map<256, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 16, kModeFront>(c, make_layout(4096, H, WPS, W, mcs, 0, true).total, ns), stream);
 						if (rc || !wide) return rc;
-						a.list = ovf[0]; a.head = cnt + 2 * 1; a.list_len = cnt + 2 * 1 + 1;
+						a.list = ovfw; a.head = sc + 2 + 3 * kSplitClasses; a.list_len = sc + 2 + 3 * kSplitClasses + 1;
 					} else {
 						// a chain set: few maps, made larger by the blend
 						a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
@@ -1011,52 +1035,70 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 					return launch_map<512, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<512, 16, kModeFront>(c, make_layout(8192, H, WPS, W, mcs, 0, true).total, set == 0 ? std::min(ns, c->n_sm) : ns), stream);
 				};
 				// Prim and back, one launch each per size class
-				auto launch_prim_back = [&](int set, cudaStream_t stream) -> int {
+				// Prim and back of one size class: two launches on `stream`
+				auto launch_class = [&](int set, int k, cudaStream_t stream) -> int {
 					const int ns = (int)sets[set].size();
-					if (ns == 0) return RVB_OK;
 					int *sc = cnt + 10 + set * kSetCounters;
 					int *lists = (int *)(M + o_cls) + (size_t)kSplitClasses * set_list_off[set];
-					const int k_first = 0;
-					for (int k = k_first; k < kSplitClasses; ++k) {
-						pa.list = lists + (size_t)k * ns; pa.list_len = sc + 2 + k; pa.head = sc + 2 + kSplitClasses + k;
-						pa.cap = split_class_cap(k);
-						const int smem = 12 * pa.cap;
-						// (warps per map, register slots per thread): 16 warps per SM in every class -- a warp issues at most
-						// every third cycle in this loop (half-rate integer pipe + dependent latency)
-						const int v = c->dense_prim ? (k < 4 ? c->prim_variant[k] : 0) : -1;
-						if (v < 0) {
-							fa.list = pa.list; fa.list_len = pa.list_len; fa.head = pa.head;
-							if (k == 0) launch_fprim<768>(c, fa, ns, H, W, stream);
-							if (k == 1) launch_fprim<1536>(c, fa, ns, H, W, stream);
-							if (k == 2) launch_fprim<2048>(c, fa, ns, H, W, stream);
-							if (k == 3) launch_fprim<3072>(c, fa, ns, H, W, stream);
-							if (k == 4) launch_fprim<4096>(c, fa, ns, H, W, stream);
-							if (k == 5) launch_fprim<8192>(c, fa, ns, H, W, stream);
-						}
-						if (k == 0 && v == 0) launch_prim<1, 24>(c, pa, ns, smem, stream);
-						if (k == 0 && v == 1) launch_prim<2, 12>(c, pa, ns, smem, stream);
-						if (k == 1 && v == 0) launch_prim<2, 24>(c, pa, ns, smem, stream);
-						if (k == 1 && v == 1) launch_prim<4, 12>(c, pa, ns, smem, stream);
-						if (k == 2 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
-						if (k == 2 && v == 1) launch_prim<4, 16>(c, pa, ns, smem, stream);
-						if (k == 3 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
-						if (k == 3 && v == 1) launch_prim<8, 12>(c, pa, ns, smem, stream);
-						if (k >= 4 && v >= 0) launch_prim<8, 16>(c, pa, ns, smem, stream);
-						CU(cudaGetLastError());
-						c->launches += 1;
-						c->map_launches += 1;
+					pa.list = lists + (size_t)k * ns; pa.list_len = sc + 2 + k; pa.head = sc + 2 + kSplitClasses + k;
+					pa.cap = split_class_cap(k);
+					const int smem = 12 * pa.cap;
+					// RVB_DENSE_PRIM=1, the round-1 all-pairs kernel: (warps per map, register slots per thread), 16 warps
+					// per SM in every class
+					const int v = c->dense_prim ? (k < 4 ? c->prim_variant[k] : 0) : -1;
+					if (v >= 0 && k >= 5) return RVB_OK;   // (no map reaches the 8192 class in that mode)
+					if (v < 0) {
+						fa.list = pa.list; fa.list_len = pa.list_len; fa.head = pa.head;
+						if (k == 0) launch_fprim<768>(c, fa, ns, H, W, stream);
+						if (k == 1) launch_fprim<1536>(c, fa, ns, H, W, stream);
+						if (k == 2) launch_fprim<2048>(c, fa, ns, H, W, stream);
+						if (k == 3) launch_fprim<3072>(c, fa, ns, H, W, stream);
+						if (k == 4) launch_fprim<4096>(c, fa, ns, H, W, stream);
+						if (k == 5) launch_fprim<8192>(c, fa, ns, H, W, stream);
 					}
-					if (set == 0) CU(cudaEventRecord(c->ev_st[1], stream));
+					if (k == 0 && v == 0) launch_prim<1, 24>(c, pa, ns, smem, stream);
+					if (k == 0 && v == 1) launch_prim<2, 12>(c, pa, ns, smem, stream);
+					if (k == 1 && v == 0) launch_prim<2, 24>(c, pa, ns, smem, stream);
+					if (k == 1 && v == 1) launch_prim<4, 12>(c, pa, ns, smem, stream);
+					if (k == 2 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
+					if (k == 2 && v == 1) launch_prim<4, 16>(c, pa, ns, smem, stream);
+					if (k == 3 && v == 0) launch_prim<4, 24>(c, pa, ns, smem, stream);
+					if (k == 3 && v == 1) launch_prim<8, 12>(c, pa, ns, smem, stream);
+					if (k >= 4 && v >= 0) launch_prim<8, 16>(c, pa, ns, smem, stream);
+					CU(cudaGetLastError());
+					c->launches += 1;
+					c->map_launches += 1;
 					a.ovf_list = nullptr; a.ovf_len = nullptr;
-					for (int k = k_first; k < kSplitClasses; ++k) {
-						a.list = lists + (size_t)k * ns; a.list_len = sc + 2 + k; a.head = sc + 2 + 2 * kSplitClasses + k;
-						int rc = RVB_OK;
-						if (k <= 1) rc = launch_map<256, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 6, kModeBack>(c, make_layout(1536, H, WPS, W, mcs, 0).total, ns), stream);
-						if (k == 2) rc = launch_map<256, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 8, kModeBack>(c, make_layout(2048, H, WPS, W, mcs, 0).total, ns), stream);
-						if (k == 3) rc = launch_map<512, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 6, kModeBack>(c, make_layout(3072, H, WPS, W, mcs, 0).total, ns), stream);
-						if (k == 4) rc = launch_map<512, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 8, kModeBack>(c, make_layout(4096, H, WPS, W, mcs, 0).total, ns), stream);
-						if (k == 5) rc = launch_map<512, 16, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 16, kModeBack>(c, make_layout(8192, H, WPS, W, mcs, 0).total, ns), stream);
+					a.list = lists + (size_t)k * ns; a.list_len = sc + 2 + k; a.head = sc + 2 + 2 * kSplitClasses + k;
+					int rc = RVB_OK;
+					if (k <= 1) rc = launch_map<256, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 6, kModeBack>(c, make_layout(1536, H, WPS, W, mcs, 0).total, ns), stream);
+					if (k == 2) rc = launch_map<256, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<256, 8, kModeBack>(c, make_layout(2048, H, WPS, W, mcs, 0).total, ns), stream);
+					if (k == 3) rc = launch_map<512, 6, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 6, kModeBack>(c, make_layout(3072, H, WPS, W, mcs, 0).total, ns), stream);
+					if (k == 4) rc = launch_map<512, 8, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 8, kModeBack>(c, make_layout(4096, H, WPS, W, mcs, 0).total, ns), stream);
+					if (k == 5) rc = launch_map<512, 16, kModeBack>(c, a, H, W, WPS, occupancy_grid<512, 16, kModeBack>(c, make_layout(8192, H, WPS, W, mcs, 0).total, ns), stream);
+					return rc;
+				};
+				// Prim and back of every size class of a set.  The classes are independent of each other, so with
+				// `fan` each runs on its own stream (forked from / joined into `stream`): a Prim launch is a latency
+				// chain per map with few warps, a back launch is barrier bound -- side by side they fill each other's
+				// idle issue slots, and the tail of one class (its largest maps) overlaps the other classes.
+				auto launch_prim_back = [&](int set, cudaStream_t stream, bool fan) -> int {
+					const int ns = (int)sets[set].size();
+					if (ns == 0) return RVB_OK;
+					if (!fan) {
+						for (int k = 0; k < kSplitClasses; ++k) {
+							const int rc = launch_class(set, k, stream);
+							if (rc) return rc;
+						}
+						return RVB_OK;
+					}
+					CU(cudaEventRecord(c->ev_cls_fork, stream));
+					for (int k = kSplitClasses - 1; k >= 0; --k) {     // largest maps first: the longest latency chains
+						CU(cudaStreamWaitEvent(c->cls_stream[k], c->ev_cls_fork, 0));
+						const int rc = launch_class(set, k, c->cls_stream[k]);
 						if (rc) return rc;
+						CU(cudaEventRecord(c->ev_cls[k], c->cls_stream[k]));
+						CU(cudaStreamWaitEvent(stream, c->ev_cls[k], 0));
 					}
 					return RVB_OK;
 				};
@@ -1068,12 +1110,13 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				cudaStream_t side = getenv("RVB_NO_SIDE") ? st : c->side_stream;
 				CU(cudaEventRecord(c->ev_fork, st));
 				CU(cudaStreamWaitEvent(side, c->ev_fork, 0));
-				if ((rc = launch_prim_back(0, st))) return rc;
+				if ((rc = launch_prim_back(0, st, !c->serial_classes))) return rc;
+				CU(cudaEventRecord(c->ev_st[1], st));      // (Prim and back of the size classes run interleaved: one stage)
 				CU(cudaEventRecord(c->ev_st[2], st));
 				c->stages_timed = !sets[0].empty();
 				for (int k = 1; k < n_sets; ++k) {
 					if ((rc = launch_front(k, side))) return rc;
-					if ((rc = launch_prim_back(k, side))) return rc;
+					if ((rc = launch_prim_back(k, side, !c->serial_classes))) return rc;
 				}
 				if ((rc = launch_mono(split_chains ? 4 : 0, side))) return rc;
 				CU(cudaEventRecord(c->ev_join, side));
@@ -1098,7 +1141,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const MapOut *d_mo = (const MapOut *)c->mapout.p;
 	uint8_t *d_empty = M + o_empty;
 
-	fill_centres_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_shots, d_mo, d_dx, d_dy, d_empty, d_status);
+	fill_centres_kernel<<<(nc * 32 + 127) / 128, 128, 0, st>>>(d_clips, nc, d_shots, d_mo, d_dx, d_dy, d_empty, d_status);
 	double *d_jumps = (double *)(M + o_jumps);
 	if (b->centres_nf) {  // dxnf, dynf: the centres before focus stability (smartVidCrop.py:2450-2451)
 		const cudaMemcpyKind knf = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
@@ -1118,19 +1161,20 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	spline_setup_kernel<<<NS, 32, (size_t)sp_doubles * sizeof(double), st>>>(d_shots, NS, d_ti, d_dx, d_dy, d_scratch, sp_doubles);
 	interp_eval_kernel<<<(NF + 255) / 256, 256, 0, st>>>(d_shots, d_fshot, NF, d_ti, d_dx, d_dy, d_scratch, d_dxi, d_dyi);
 	const int lp_doubles = (int)std::min<long long>(max_lp_doubles, 6144);
+	double *d_minmax = (double *)(M + o_minmax);
 	lowpass_kernel<<<2 * NS, 32, (size_t)lp_doubles * sizeof(double), st>>>(d_shots, NS, d_clips, (const FilterCoef *)(M + o_coefs),
-													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt, lp_doubles);
+													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt, lp_doubles, d_minmax);
 	{
 		const long long warps = 2LL * NF;
 		const int blocks = (int)((warps * 32 + 255) / 256);
 		smooth_kernel<<<blocks, 256, 0, st>>>(d_shots, d_fshot, NF, d_clips, d_dxl, d_dyl, d_dxs, d_dys, p->loess_filt,
-											  p->loess_w_secs, p->loess_degree);
+											  p->loess_w_secs, p->loess_degree, d_minmax);
 	}
 	int32_t *d_dims = (int32_t *)(M + o_dims);
 	boxes_kernel<<<(int)(((long long)NF * R + 255) / 256), 256, 0, st>>>(d_clips, d_fclip, NF, R, (const int *)(M + o_final),
 																		d_borders, H, W, d_dxs, d_dys, p->shift_time, d_boxes, d_dims);
 	double *d_cscore = (double *)(M + o_cscore), *d_mscore = (double *)(M + o_mscore);
-	clip_scores_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_mo, H, W, R, d_mscore, d_cscore);
+	clip_scores_kernel<<<(nc * 32 + 127) / 128, 128, 0, st>>>(d_clips, nc, d_mo, H, W, R, p->exit_on_low_cvrg, d_mscore, d_cscore);
 	CU(cudaGetLastError());
 	c->launches += 7;
 
@@ -1177,7 +1221,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	if (!c || !b) return fail(RVB_ERR_INVALID, "NULL argument");
 	if (b->n_videos < 1 || b->n_users < 1 || b->n_users > 64) return fail(RVB_ERR_INVALID, "n_videos=%d n_users=%d", b->n_videos, b->n_users);
-	if (!b->frame_offset || !b->n_eval || !b->method_boxes || !b->annot_boxes || !b->acc) return fail(RVB_ERR_INVALID, "NULL array");
+	if (!b->frame_offset || (!b->n_eval && !b->n_eval_user) || !b->method_boxes || !b->annot_boxes || !b->acc) return fail(RVB_ERR_INVALID, "NULL array");
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
 	const bool host = b->mem_space == RVB_MEM_HOST;
@@ -1185,14 +1229,17 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	const long long NF = b->frame_offset[V];
 	if (NF < 1 || b->frame_offset[0] != 0) return fail(RVB_ERR_INVALID, "frame_offset must start at 0");
 	if (NF > 0x7fffffffLL) return fail(RVB_ERR_INVALID, "more than 2^31 frames in one call");
-	std::vector<int> first(V + 1), neval(V);
+	std::vector<int> first(V + 1), neval((size_t)V * U);
 	long long max_frames = 1;
 	for (int v = 0; v < V; ++v) {
 		const long long f0 = b->frame_offset[v], f1 = b->frame_offset[v + 1];
 		if (f1 < f0) return fail(RVB_ERR_INVALID, "frame_offset not monotone");
-		if (b->n_eval[v] < 1 || b->n_eval[v] > f1 - f0) return fail(RVB_ERR_INVALID, "video %d: n_eval=%d of %lld frames", v, b->n_eval[v], f1 - f0);
+		for (int u = 0; u < U; ++u) {
+			const int ne = b->n_eval_user ? b->n_eval_user[(size_t)v * U + u] : b->n_eval[v];
+			if (ne < 1 || ne > f1 - f0) return fail(RVB_ERR_INVALID, "video %d: n_eval=%d of %lld frames", v, ne, f1 - f0);
+			neval[(size_t)v * U + u] = ne;
+		}
 		first[v] = (int)f0;
-		neval[v] = b->n_eval[v];
 		max_frames = std::max(max_frames, f1 - f0);
 	}
 	Staging sg;
@@ -1200,8 +1247,9 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	const long long chunks = (max_frames + 255) / 256;
 	if (chunks > 65535) return fail(RVB_ERR_INVALID, "a video of %lld frames (max 16.7 M per video)", max_frames);
 	const size_t o_first = sg.add(first.data(), (size_t)(V + 1) * sizeof(int));
-	const size_t o_ne = sg.add(neval.data(), (size_t)V * sizeof(int));
+	const size_t o_ne = sg.add(neval.data(), (size_t)V * U * sizeof(int));
 	const size_t o_acc = sg.add(nullptr, (size_t)V * U * 2 * sizeof(uint64_t));
+	const size_t o_bad = sg.add(nullptr, sizeof(int));
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
 	if (c->stage.ensure(sg.bytes.size()) || c->iou_a.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
 	memcpy(c->stage.p, sg.bytes.data(), sg.bytes.size());
@@ -1225,15 +1273,23 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	}
 	unsigned long long *d_acc = (unsigned long long *)(M + o_acc);
 	CU(cudaMemsetAsync(d_acc, 0, (size_t)V * U * 2 * sizeof(uint64_t), st));
+	int *d_bad = (int *)(M + o_bad);
+	CU(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
 	iou_kernel<<<dim3((unsigned)V, (unsigned)chunks), 256, 0, st>>>(d_method, d_annot, (const int *)(M + o_first),
-															(const int *)(M + o_ne), NF, U, d_fiou, d_acc);
+															(const int *)(M + o_ne), NF, U, d_fiou, d_acc, d_bad);
 	CU(cudaGetLastError());
 	c->launches += 1;
 	const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
 	CU(cudaMemcpyAsync(b->acc, d_acc, (size_t)V * U * 2 * sizeof(uint64_t), kind, st));
+	if (b->n_bad) CU(cudaMemcpyAsync(b->n_bad, d_bad, sizeof(int), kind, st));
 	if (host) {
 		if (b->frame_iou) CU(cudaMemcpyAsync(b->frame_iou, d_fiou, (size_t)NF * U * sizeof(double), kind, st));
+		int n_bad = 0;
+		CU(cudaMemcpyAsync(&n_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
+		// malformed boxes (x2 < x1 or an empty union): the reference averages a negative value or raises
+		// ZeroDivisionError (retargetvid_eval.py:24-26); neither fits the exact accumulator, so the call says so
+		if (n_bad > 0) return fail(RVB_ERR_INVALID, "%d IoU(s) outside [0, 1]: a box with x2 < x1 / y2 < y1 or an empty union", n_bad);
 	}
 	return RVB_OK;
 }
@@ -1354,6 +1410,7 @@ extern "C" int rvb_debug_smooth_series(rvb_ctx *c, const rvb_params *p, const do
 	const size_t o_xl = sg.add(nullptr, (size_t)n * sizeof(double)), o_yl = sg.add(nullptr, (size_t)n * sizeof(double));
 	const size_t o_xs = sg.add(nullptr, (size_t)n * sizeof(double)), o_ys = sg.add(nullptr, (size_t)n * sizeof(double));
 	const size_t o_scr = sg.add(nullptr, (size_t)(2 * (n + 6 * (RVB_MAX_LP_ORDER + 1)) + 16) * sizeof(double));
+	const size_t o_mm = sg.add(nullptr, 4 * sizeof(double));
 	if (c->misc.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
 	uint8_t *D = (uint8_t *)c->misc.p;
 	CU(cudaMemcpyAsync(D, sg.bytes.data(), sg.bytes.size(), cudaMemcpyHostToDevice, st));
@@ -1361,11 +1418,11 @@ extern "C" int rvb_debug_smooth_series(rvb_ctx *c, const rvb_params *p, const do
 	const int dbg_lp_doubles = std::min(n + 6 * (RVB_MAX_LP_ORDER + 1), 6144);
 	lowpass_kernel<<<2, 32, (size_t)dbg_lp_doubles * sizeof(double), st>>>((const ShotDev *)(D + o_sh), 1, (const ClipDev *)(D + o_cl), (const FilterCoef *)(D + o_fc),
 									  (const int *)(D + o_cc), (const double *)(D + o_x), (const double *)(D + o_y),
-									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt, dbg_lp_doubles);
+									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt, dbg_lp_doubles, (double *)(D + o_mm));
 	const int blocks = (int)((2LL * n * 32 + 255) / 256);
 	smooth_kernel<<<blocks, 256, 0, st>>>((const ShotDev *)(D + o_sh), (const int *)(D + o_fs), n, (const ClipDev *)(D + o_cl),
 										  (const double *)(D + o_xl), (const double *)(D + o_yl), (double *)(D + o_xs),
-										  (double *)(D + o_ys), p->loess_filt, p->loess_w_secs, p->loess_degree);
+										  (double *)(D + o_ys), p->loess_filt, p->loess_w_secs, p->loess_degree, (const double *)(D + o_mm));
 	CU(cudaGetLastError());
 	c->launches += 2;
 	if (lowpassed_out) CU(cudaMemcpyAsync(lowpassed_out, D + o_xl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));

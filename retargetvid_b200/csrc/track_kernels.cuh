@@ -33,49 +33,60 @@ struct FilterCoef {        // Butterworth low-pass in transfer-function form + l
 };
 
 // ---------------------------------------------------------------------------------------------
-// a9: sc_handle_empty_centers, smartVidCrop.py:1221-1300.  One thread per clip.
+// a9: sc_handle_empty_centers, smartVidCrop.py:1221-1300.  One warp per clip: the lanes copy the per-map centres out of
+// the map records in parallel; only a clip that has an empty map (no salient pixel left) runs the reference's
+// sequential fill, on one lane.
 // ---------------------------------------------------------------------------------------------
-__global__ void fill_centres_kernel(const ClipDev *clips, int n_clips, const ShotDev *shots, const MapOut *mo,
-									double *dx, double *dy, uint8_t *empty, int *clip_status) {
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) fill_centres_kernel(const ClipDev *clips, int n_clips, const ShotDev *shots, const MapOut *mo,
+															double *dx, double *dy, uint8_t *empty, int *clip_status) {
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (c >= n_clips) return;
 	const ClipDev cl = clips[c];
 	const int N = cl.n_maps, base = cl.map_offset;
-	int status = 0;
-	for (int i = 0; i < N; ++i) {
+	bool cap = false, any_empty = false;
+	for (int i = lane; i < N; i += 32) {
 		const MapOut &o = mo[base + i];
-		const bool e = (o.flags & kFlagEmpty) != 0;
-		if (o.flags & (kFlagOverflow | kFlagClusterCapacity)) status = RVB_ERR_CAPACITY;
+		const int fl = o.flags;
+		const bool e = (fl & kFlagEmpty) != 0;
+		cap |= (fl & (kFlagOverflow | kFlagClusterCapacity)) != 0;
+		any_empty |= e;
 		if (empty) empty[base + i] = e ? 1 : 0;
 		dx[base + i] = e ? nan("") : o.cx;
 		dy[base + i] = e ? nan("") : o.cy;
 	}
-	int i = 0;
-	while (i < N) {
-		if (!isnan(dx[base + i])) { ++i; continue; }
-		int j = i;
-		while (j + 1 < N && isnan(dx[base + j + 1])) ++j;  // empty run [i, j]
-		int d_start = 0x7fffffff, d_end = 0x7fffffff;
-		for (int s = 0; s < cl.n_shots; ++s) {
-			const ShotDev &sh = shots[cl.shot_offset + s];
-			d_start = min(d_start, abs(sh.m0 - i));
-			d_end = min(d_end, abs(sh.m1 - j));
+	cap = __any_sync(0xffffffffu, cap);
+	any_empty = __any_sync(0xffffffffu, any_empty);
+	int status = cap ? RVB_ERR_CAPACITY : 0;
+	__syncwarp();
+	if (any_empty && lane == 0) {
+		int i = 0;
+		while (i < N) {
+			if (!isnan(dx[base + i])) { ++i; continue; }
+			int j = i;
+			while (j + 1 < N && isnan(dx[base + j + 1])) ++j;  // empty run [i, j]
+			int d_start = 0x7fffffff, d_end = 0x7fffffff;
+			for (int s = 0; s < cl.n_shots; ++s) {
+				const ShotDev &sh = shots[cl.shot_offset + s];
+				d_start = min(d_start, abs(sh.m0 - i));
+				d_end = min(d_end, abs(sh.m1 - j));
+			}
+			double xf, yf;
+			if (d_start < d_end) {  // closer to a shot start: take the next value
+				xf = dx[base + j + 1];
+				yf = dy[base + j + 1];
+			} else {                // else the previous one (python's dx[-1] when the run starts at 0)
+				const int k = (i == 0) ? (N - 1) : (i - 1);
+				xf = dx[base + k];
+				yf = dy[base + k];
+			}
+			for (int k = i; k <= j; ++k) { dx[base + k] = xf; dy[base + k] = yf; }
+			i = j + 1;
 		}
-		double xf, yf;
-		if (d_start < d_end) {  // closer to a shot start: take the next value
-			xf = dx[base + j + 1];
-			yf = dy[base + j + 1];
-		} else {                // else the previous one (python's dx[-1] when the run starts at 0)
-			const int k = (i == 0) ? (N - 1) : (i - 1);
-			xf = dx[base + k];
-			yf = dy[base + k];
-		}
-		for (int k = i; k <= j; ++k) { dx[base + k] = xf; dy[base + k] = yf; }
-		i = j + 1;
+		for (int k = 0; k < N; ++k)
+			if (isnan(dx[base + k]) && status == 0) status = RVB_ERR_NO_CENTRES;
 	}
-	for (int k = 0; k < N; ++k)
-		if (isnan(dx[base + k]) && status == 0) status = RVB_ERR_NO_CENTRES;
-	clip_status[c] = status;
+	if (lane == 0) clip_status[c] = status;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,18 +328,37 @@ __global__ void interp_eval_kernel(const ShotDev *shots, const int *frame_shot, 
 // reference's moving-average fallback when filtfilt raises (shots of <= padlen frames).
 // One thread per (shot, axis).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double df2t_step(const FilterCoef &fc, double *z, double x) {
-	const int m = fc.order;
-	const double y = __dadd_rn(z[0], __dmul_rn(fc.b[0], x));
-	for (int i = 0; i < m - 1; ++i)
-		z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(x, fc.b[i + 1])), __dmul_rn(y, fc.a[i + 1]));
-	z[m - 1] = __dsub_rn(__dmul_rn(x, fc.b[m]), __dmul_rn(y, fc.a[m]));
-	return y;
+// forward and backward pass of filtfilt over buf[0 .. ne), direct form II transposed, with the state and the
+// coefficients in registers (the order is a compile-time constant: no local-memory array on the serial chain)
+template <int M>
+__device__ __forceinline__ void filtfilt_inplace(const FilterCoef &fc, double *buf, int ne) {
+	double b[M + 1], a[M + 1], zi[M], z[M];
+#pragma unroll
+	for (int i = 0; i <= M; ++i) { b[i] = fc.b[i]; a[i] = fc.a[i]; }
+#pragma unroll
+	for (int i = 0; i < M; ++i) zi[i] = fc.zi[i];
+	auto step = [&](double x) -> double {
+		const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
+#pragma unroll
+		for (int i = 0; i < M - 1; ++i) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(x, b[i + 1])), __dmul_rn(y, a[i + 1]));
+		z[M - 1] = __dsub_rn(__dmul_rn(x, b[M]), __dmul_rn(y, a[M]));
+		return y;
+	};
+	const double e0 = buf[0];
+#pragma unroll
+	for (int i = 0; i < M; ++i) z[i] = zi[i] * e0;
+	for (int i = 0; i < ne; ++i) buf[i] = step(buf[i]);
+	const double y0 = buf[ne - 1];
+#pragma unroll
+	for (int i = 0; i < M; ++i) z[i] = zi[i] * y0;
+	for (int i = ne - 1; i >= 0; --i) buf[i] = step(buf[i]);
 }
 
+// also leaves min / max of the low-passed series of every (shot, axis) in shot_minmax[(shot * 2 + axis) * 2 + {0, 1}]:
+// the LOESS stage normalises by them (pyloess.py:16-24) and would otherwise rescan the shot for every output frame
 __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n_shots, const ClipDev *clips, const FilterCoef *coefs,
 													  const int *clip_coef, const double *dxi, const double *dyi, double *dxl, double *dyl,
-													  double *scratch, int lp_filt, int smem_doubles) {
+													  double *scratch, int lp_filt, int smem_doubles, double *shot_minmax) {
 	extern __shared__ double lp_smem[];
 	const int id = blockIdx.x, lane = threadIdx.x;
 	if (id >= n_shots * 2) return;
@@ -337,14 +367,13 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 	const int cl = sh.f1 - sh.f0 + 1;
 	const double *x = (axis ? dyi : dxi) + sh.frame_base;
 	double *out = (axis ? dyl : dxl) + sh.frame_base;
-	if (!lp_filt) {
-		for (int i = lane; i < cl; i += 32) out[i] = x[i];
-		return;
-	}
+	double vmin = INFINITY, vmax = -INFINITY;
 	const FilterCoef &fc = coefs[clip_coef[sh.clip]];
 	const int m = fc.order;
 	const int edge = 3 * (m + 1);
-	if (m > 0 && cl > edge) {
+	if (!lp_filt) {
+		for (int i = lane; i < cl; i += 32) { const double v = x[i]; out[i] = v; vmin = fmin(vmin, v); vmax = fmax(vmax, v); }
+	} else if (m > 0 && cl > edge) {
 		// odd extension (lanes in parallel), forward pass in place, backward pass in place (lane 0), copy out
 		const int ne = cl + 2 * edge;
 		double *buf = (ne <= smem_doubles) ? lp_smem : (scratch + sh.scratch_base + (size_t)axis * ne);
@@ -357,24 +386,34 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 		}
 		__syncwarp();
 		if (lane == 0) {
-			double z[RVB_MAX_LP_ORDER];
-			const double e0 = buf[0];
-			for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * e0;
-			for (int i = 0; i < ne; ++i) buf[i] = df2t_step(fc, z, buf[i]);
-			const double y0 = buf[ne - 1];
-			for (int i = 0; i < m; ++i) z[i] = fc.zi[i] * y0;
-			for (int i = ne - 1; i >= 0; --i) buf[i] = df2t_step(fc, z, buf[i]);
+			switch (m) {
+			case 1: filtfilt_inplace<1>(fc, buf, ne); break;
+			case 2: filtfilt_inplace<2>(fc, buf, ne); break;
+			case 3: filtfilt_inplace<3>(fc, buf, ne); break;
+			case 4: filtfilt_inplace<4>(fc, buf, ne); break;
+			case 5: filtfilt_inplace<5>(fc, buf, ne); break;
+			case 6: filtfilt_inplace<6>(fc, buf, ne); break;
+			case 7: filtfilt_inplace<7>(fc, buf, ne); break;
+			default: filtfilt_inplace<8>(fc, buf, ne); break;
+			}
 		}
 		__syncwarp();
-		for (int i = lane; i < cl; i += 32) out[i] = buf[edge + i];
-		return;
+		for (int i = lane; i < cl; i += 32) { const double v = buf[edge + i]; out[i] = v; vmin = fmin(vmin, v); vmax = fmax(vmax, v); }
+	} else {
+		// fallback: 5-tap moving average of the interior, edges untouched (smartVidCrop.py:1611-1615)
+		for (int i = lane; i < cl; i += 32) {
+			double v = x[i];
+			if (cl >= 5 && i >= 2 && i < cl - 2) v = ((((x[i - 2] + x[i - 1]) + x[i]) + x[i + 1]) + x[i + 2]) / 5.0;
+			out[i] = v;
+			vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+		}
 	}
-	// fallback: 5-tap moving average of the interior, edges untouched (smartVidCrop.py:1611-1615)
-	for (int i = lane; i < cl; i += 32) {
-		double v = x[i];
-		if (cl >= 5 && i >= 2 && i < cl - 2) v = ((((x[i - 2] + x[i - 1]) + x[i]) + x[i + 1]) + x[i + 2]) / 5.0;
-		out[i] = v;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+		vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
 	}
+	if (lane == 0 && shot_minmax != nullptr) { shot_minmax[(size_t)id * 2] = vmin; shot_minmax[(size_t)id * 2 + 1] = vmax; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,12 +432,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n_frames_total, const ClipDev *clips,
 							  const double *dxl, const double *dyl, double *dxs, double *dys, int loess_filt,
-							  double loess_w_secs, int degree) {
+							  double loess_w_secs, int degree, const double *shot_minmax) {
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (gw >= n_frames_total * 2) return;
 	const int f = gw >> 1, axis = gw & 1;
-	const ShotDev sh = shots[frame_shot[f]];
+	const int shot = frame_shot[f];
+	const ShotDev sh = shots[shot];
 	const int cl = sh.f1 - sh.f0 + 1;
 	const int j = f - sh.frame_base;
 	const double *y = (axis ? dyl : dxl) + sh.frame_base;
@@ -414,17 +454,9 @@ __global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n
 	int lo = j - h;
 	if (lo < 0) lo = 0;
 	if (lo + win > cl) lo = cl - win;
-	// normalisation of y (pyloess.py:16-24); a constant series divides by zero -> NaN -> identity
-	double ymin = INFINITY, ymax = -INFINITY;
-	for (int i = lane; i < cl; i += 32) {
-		ymin = fmin(ymin, y[i]);
-		ymax = fmax(ymax, y[i]);
-	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-		ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-	}
+	// normalisation of y (pyloess.py:16-24); a constant series divides by zero -> NaN -> identity.  The shot's min / max
+	// come from the low-pass kernel.
+	const double ymin = shot_minmax[((size_t)shot * 2 + axis) * 2], ymax = shot_minmax[((size_t)shot * 2 + axis) * 2 + 1];
 	if (loess_filt && !(ymax > ymin)) {
 		if (lane == 0) out[j] = y[j];
 		return;
@@ -574,24 +606,31 @@ __global__ void boxes_kernel(const ClipDev *clips, const int *frame_clip, int n_
 	}
 }
 
-// per-clip scores: mean saliency of the raw maps and mean coverage per ratio
-__global__ void clip_scores_kernel(const ClipDev *clips, int n_clips, const MapOut *mo, int H, int W, int n_ratios,
-								   double *map_scores, double *clip_scores) {
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// per-clip scores: mean saliency of the raw maps and mean coverage per ratio.  One warp per clip: the raw sums are exact
+// integers (any order); the coverage means are float64 sums in map order as the reference takes them
+// (smartVidCrop.py:1326-1329), kept sequential on one lane and only computed when the coverage score is on.
+__global__ void __launch_bounds__(128) clip_scores_kernel(const ClipDev *clips, int n_clips, const MapOut *mo, int H, int W, int n_ratios,
+														   int with_cvrg, double *map_scores, double *clip_scores) {
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (c >= n_clips) return;
 	const ClipDev cl = clips[c];
 	unsigned long long tot = 0;
-	double cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-	for (int i = 0; i < cl.n_maps; ++i) {
-		const MapOut &o = mo[cl.map_offset + i];
-		tot += o.raw_sum;
-		if (map_scores) map_scores[cl.map_offset + i] = (double)o.raw_sum / (double)(H * W);
-		for (int r = 0; r < n_ratios; ++r) cv[r] += o.cvrg[r];
+	for (int i = lane; i < cl.n_maps; i += 32) {
+		const unsigned int rs = mo[cl.map_offset + i].raw_sum;
+		tot += rs;
+		if (map_scores) map_scores[cl.map_offset + i] = (double)rs / (double)(H * W);
 	}
-	if (clip_scores) {
-		double *o = clip_scores + (size_t)c * (1 + n_ratios);
-		o[0] = (double)tot / ((double)H * (double)W * (double)cl.n_maps);
-		for (int r = 0; r < n_ratios; ++r) o[1 + r] = cv[r] / (double)cl.n_maps;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+	if (lane == 0 && clip_scores) {
+		double *out = clip_scores + (size_t)c * (1 + n_ratios);
+		out[0] = (double)tot / ((double)H * (double)W * (double)cl.n_maps);
+		double cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		if (with_cvrg)
+			for (int i = 0; i < cl.n_maps; ++i)
+				for (int r = 0; r < n_ratios; ++r) cv[r] += mo[cl.map_offset + i].cvrg[r];
+		for (int r = 0; r < n_ratios; ++r) out[1 + r] = cv[r] / (double)cl.n_maps;
 	}
 }
 

@@ -62,22 +62,22 @@ def evaluate_arrays(ctx, method, annots, frame_counts, want_frame_iou=False):
 	U = len(annots)
 	V = len(vids)
 	offs = np.zeros(V + 1, dtype=np.int64)
-	neval = np.zeros(V, dtype=np.int32)
+	neval = np.zeros((V, U), dtype=np.int32)
 	for i, v in enumerate(vids):
-		# the reference stops at the first frame either list lacks (retargetvid_eval.py:163-179)
-		n = min([int(frame_counts[v]), len(method[v])] + [len(a[v]) for a in annots])
-		if n < 1:
-			raise statistics.StatisticsError('mean requires at least one data point')
-		neval[i] = n
-		offs[i + 1] = offs[i] + n
-	NF = int(offs[V])
-	mb = np.empty((NF, 4), dtype=np.int32)
-	ab = np.empty((U, NF, 4), dtype=np.int32)
-	for i, v in enumerate(vids):
-		n = neval[i]
-		mb[offs[i]:offs[i + 1]] = method[v][:n]
+		# the reference stops, per annotator, at the first frame either list lacks (retargetvid_eval.py:163-179)
 		for u in range(U):
-			ab[u, offs[i]:offs[i + 1]] = annots[u][v][:n]
+			n = min(int(frame_counts[v]), len(method[v]), len(annots[u][v]))
+			if n < 1:
+				raise statistics.StatisticsError('mean requires at least one data point')
+			neval[i, u] = n
+		offs[i + 1] = offs[i] + int(neval[i].max())
+	NF = int(offs[V])
+	mb = np.zeros((NF, 4), dtype=np.int32)
+	ab = np.zeros((U, NF, 4), dtype=np.int32)
+	for i, v in enumerate(vids):
+		mb[offs[i]:offs[i] + int(neval[i].max())] = method[v][:int(neval[i].max())]
+		for u in range(U):
+			ab[u, offs[i]:offs[i] + neval[i, u]] = annots[u][v][:neval[i, u]]
 	acc = np.zeros((V, U, 2), dtype=np.uint64)
 	fiou = np.empty((U, NF), dtype=np.float64) if want_frame_iou else None
 	b = _cabi.rvb_iou_batch()
@@ -85,13 +85,15 @@ def evaluate_arrays(ctx, method, annots, frame_counts, want_frame_iou=False):
 	b.n_users = U
 	b.mem_space = _cabi.RVB_MEM_HOST
 	b.frame_offset = offs.ctypes.data
-	b.n_eval = neval.ctypes.data
+	b.n_eval = None
+	b.n_eval_user = neval.ctypes.data
 	b.method_boxes = mb.ctypes.data
 	b.annot_boxes = ab.ctypes.data
 	b.frame_iou = fiou.ctypes.data if want_frame_iou else None
 	b.acc = acc.ctypes.data
+	# malformed boxes (x2 < x1, empty union) make the call fail loudly: RvbError(RVB_ERR_INVALID)
 	ctx.iou_batch(b)
-	vid_iou = [[ctx.iou_mean_from_acc(acc[i, u, 0], acc[i, u, 1], int(neval[i])) for u in range(U)] for i in range(V)]
+	vid_iou = [[ctx.iou_mean_from_acc(acc[i, u, 0], acc[i, u, 1], int(neval[i, u])) for u in range(U)] for i in range(V)]
 	return vid_iou, fiou, vids
 
 
@@ -139,6 +141,25 @@ def main(argv=None):
 	print(' ...found annotations from %d users' % len(annots))
 	frame_counts = {v: len(annots[0]['1-3'][v]) for v in VID_INDS}
 	runs = sorted(os.path.split(f)[-1] for f in os.scandir(runs_folder) if f.is_dir())
+	# validity report of the reference (retargetvid_eval.py:102-121): counted, never rejected
+	print(' Checking runs validity...')
+	for run in runs:
+		file_errors_count = 0
+		frame_count_errors_count = 0
+		for v in VID_INDS:
+			for ar in ARS:
+				fn = os.path.join(runs_folder, run, '%03d_%s.txt' % (v, ar))
+				if not os.path.isfile(fn):
+					file_errors_count += 1
+				else:
+					with open(fn) as fp:
+						n_lines = len(fp.read().splitlines())
+					if abs(frame_counts[v] - n_lines) > 1:
+						frame_count_errors_count += 1
+		print(' - %-30s (file errors:%d + frame count errors:%d)' % (run, file_errors_count, frame_count_errors_count))
+	print(' valid runs::')
+	for run in runs:
+		print(' - %s' % run)
 	ctx = _cabi.Context(0)
 	lines = []
 	header = ('%-36s' + ',%-6s' * 23) % ('Method', 'Worst', 'Best', 'Mean', 'ttm', 'tta', 'tcm', 'tca', 'ccm', 'cca',

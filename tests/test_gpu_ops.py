@@ -1,0 +1,196 @@
+"""GPU tests of the entry points around the kernels: the torch custom op fed with device-resident tensors on the
+caller's stream, per-video sharding over several GPUs (8e), per-clip error isolation in a batch, and
+the lattice-local Prim against the all-pairs Prim.  Needs a GPU: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def engine():
+	from retargetvid_b200.engine import CropEngine
+	e = CropEngine(0)
+	yield e
+	e.close()
+
+
+def _clips(n, seed0=7700):
+	from retargetvid_b200 import synth
+	return [synth.make_clip(seed0 + i, fc=70 + 23 * i, shot_starts=[31] if i % 2 else [], keep_logp=True) for i in range(n)]
+
+
+def test_torch_op_device_tensors_on_caller_stream(engine):
+	"""torch.ops.retargetvid_b200.crop_track: uint8 [N,H,256] and float32 log-saliency [N,H,W] tensors that live on the
+	device (where UNISAL leaves them, unisal/train.py:852-854 before the .cpu()), launched on a non-default stream:
+	same boxes and centres as the host-buffer path, and nothing but the status leaves the device."""
+	import torch
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import torch_op
+	vds = _clips(4)
+	CP = svc.sc_init_crop_params()
+	ratios = ['1:3', '9:16']
+	want = engine.run(vds, CP, ratios, detail=True)
+	want_boxes = np.concatenate([w.boxes for w in want], axis=1)
+	want_dx = np.concatenate([w.dx for w in want])
+	st = torch.cuda.Stream()
+	with torch.cuda.stream(st):
+		u8 = torch.zeros((sum(v['fc_sel'] for v in vds), 140, 256), dtype=torch.uint8, device='cuda')
+		mo = 0
+		for vd in vds:
+			n = vd['fc_sel']
+			u8[mo:mo + n, :, :250] = torch.from_numpy(np.ascontiguousarray(np.transpose(vd['smaps'], (2, 0, 1)))).cuda()
+			u8[mo:mo + n, :, 250:] = 99          # row padding is the producer's garbage
+			mo += n
+		boxes, centres, status = torch_op.crop_track(u8, vds, CP, ratios)
+		assert boxes.is_cuda and centres.is_cuda and boxes.dtype == torch.int32
+		f32 = torch.from_numpy(np.ascontiguousarray(np.concatenate([vd['_logp'] for vd in vds]), dtype=np.float32)).cuda()
+		boxes_f, centres_f, status_f = torch_op.crop_track(f32, vds, CP, ratios)
+	st.synchronize()
+	assert status.cpu().tolist() == [0] * len(vds) and status_f.cpu().tolist() == [0] * len(vds)
+	assert np.array_equal(boxes.cpu().numpy(), want_boxes)
+	assert np.array_equal(centres.cpu().numpy()[0], want_dx)
+	# float32 entry: the fused uint8 post-process may differ from numpy's by one grey level on a few pixels
+	# (tests/test_gpu_parity.py::test_float32_entry); on these clips the boxes are the same
+	assert np.array_equal(boxes_f.cpu().numpy(), want_boxes)
+
+
+def test_multi_gpu_sharded_equals_single_gpu(engine):
+	"""smart_vid_crop_batch(devices=[0, 1]): per-video LPT shards, one context and host thread per GPU, results gathered
+	on the host in input order == the single-GPU result."""
+	import torch
+	if torch.cuda.device_count() < 2:
+		pytest.skip('needs 2 GPUs')
+	from retargetvid_b200 import smartVidCrop as svc
+	vds = _clips(9, seed0=7800)
+	CP = svc.sc_init_crop_params()
+	ratios = ['1:3', '3:1', '4:5']
+	one = svc.smart_vid_crop_batch(vds, CP, ratios, device=0)
+	two = svc.smart_vid_crop_batch(vds, CP, ratios, devices=[0, 1])
+	for a, b in zip(one, two):
+		assert a.status == 0 and b.status == 0
+		assert np.array_equal(a.boxes, b.boxes) and np.array_equal(a.dx, b.dx) and np.array_equal(a.series, b.series)
+
+
+def test_one_failing_clip_does_not_take_the_batch_down(engine):
+	"""A clip with a map of more salient pixels than RVB_MAX_POINTS reports RVB_ERR_CAPACITY for itself; the other
+	clips of the batch keep results identical to running them alone (the reference's loop would also only lose that
+	one video)."""
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	vds = _clips(3, seed0=7900)
+	bad = dict(vds[1])
+	sm = bad['smaps'].copy()
+	sm[:, :, 2] = 200          # 35 000 salient pixels in one map
+	bad['smaps'] = sm
+	batch = [vds[0], bad, vds[2]]
+	CP = svc.sc_init_crop_params()
+	res = svc.smart_vid_crop_batch(batch, CP, ['1:3'])
+	assert res[1].status == _cabi.RVB_ERR_CAPACITY
+	for i in (0, 2):
+		alone = svc.smart_vid_crop_batch([batch[i]], CP, ['1:3'])[0]
+		assert res[i].status == 0 and np.array_equal(res[i].boxes, alone.boxes)
+	with pytest.raises(_cabi.RvbError):
+		svc.smart_vid_crop_batch(batch, CP, ['1:3'], raise_on_clip_error=True)
+
+
+def test_lattice_local_prim_equals_all_pairs_prim():
+	"""fprim_kernel (lattice offsets + bucket queue + lazy far keys) against the round-1 all-pairs prim_kernel
+	(the default; RVB_FRONTIER_PRIM=1 selects the lattice-local one) on blobs, salt noise (every step a stall), sparse maps, cuts (blended chain maps) and the
+	min_cluster_size 5 / min_samples 3 setting (core distances below 9): identical filtered maps, per-map records,
+	centres and boxes."""
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	from retargetvid_b200.engine import CropEngine
+	vds = [synth.make_clip(8000 + i, fc=90 + 11 * i, shot_starts=[40, 47] if i % 2 else []) for i in range(6)]
+	vds += [synth.make_clip(8100, fc=60, kind='noise', shot_starts=[25]), synth.make_clip(8101, fc=50, kind='few_points'),
+			synth.make_clip(8102, fc=40, kind='single_pixel'), synth.make_clip(8103, fc=45, kind='constant')]
+	outs = {}
+	for over in ({}, dict(hdbscan_min=5, hdbscan_min_samples=3, t_threshold=90, select_sum=1)):
+		CP = svc.sc_init_crop_params()
+		CP.update(over)
+		for dense in (True, False):
+			if dense:
+				os.environ.pop('RVB_FRONTIER_PRIM', None)
+			else:
+				os.environ['RVB_FRONTIER_PRIM'] = '1'
+			e = CropEngine(0)
+			try:
+				outs[dense] = e.run(vds, CP, ['1:3', '3:1'], detail=True, want_filtered=True, raise_on_clip_error=False)
+			finally:
+				e.close()
+				os.environ.pop('RVB_FRONTIER_PRIM', None)
+		for i, (a, b) in enumerate(zip(outs[True], outs[False])):
+			assert a.status == b.status, i
+			assert np.array_equal(a.filtered, b.filtered), (i, over)
+			assert np.array_equal(a.map_info, b.map_info), (i, over)
+			assert np.array_equal(a.boxes, b.boxes) and np.array_equal(a.dx, b.dx, equal_nan=True), (i, over)
+
+
+def _write_boxes(path, boxes):
+	with open(path, 'w') as fp:
+		fp.write(''.join('%d,%d,%d,%d\n' % tuple(int(v) for v in b) for b in boxes))
+
+
+def test_evaluator_cli_reproduces_the_reference_csv(tmp_path, capsys, monkeypatch):
+	"""python -m retargetvid_b200.retargetvid_eval on the shipped results + the 6 annotators (written out from the
+	committed fixture): the CSV line the unmodified retargetvid_eval.py prints, and its validity
+	report (retargetvid_eval.py:102-121)."""
+	from helpers import GOLDEN
+	from retargetvid_b200 import retargetvid_eval as rev
+	z = np.load(os.path.join(GOLDEN, 'eval_fixture.npz'))
+	vids = [int(v) for v in z['vid_inds']]
+	ann_dir = tmp_path / 'annotations'
+	res_dir = tmp_path / 'results' / 'smartvidcrop'
+	res_dir.mkdir(parents=True)
+	for u in range(1, 7):
+		d = ann_dir / ('annotator_%d' % u)
+		d.mkdir(parents=True)
+		for ar in ('1-3', '3-1'):
+			lens = z['annot_len_%d_%s' % (u, ar)]
+			offs = np.concatenate([[0], np.cumsum(lens)])
+			boxes = z['annot_%d_%s' % (u, ar)]
+			for i, v in enumerate(vids):
+				_write_boxes(d / ('%03d_%s.txt' % (v, ar)), boxes[offs[i]:offs[i + 1]])
+	for ar in ('1-3', '3-1'):
+		lens = z['method_len_%s' % ar]
+		offs = np.concatenate([[0], np.cumsum(lens)])
+		boxes = z['method_%s' % ar]
+		for i, v in enumerate(vids):
+			_write_boxes(res_dir / ('%03d_%s.txt' % (v, ar)), boxes[offs[i]:offs[i + 1]])
+	monkeypatch.chdir(tmp_path)
+	lines = rev.main([str(tmp_path / 'results'), '--annotations', str(ann_dir)])
+	want = str(z['eval_csv']).splitlines()[-1].split(',')
+	got = lines[-1].split(',')
+	assert got[1:4] == want[1:4] and got[12:15] == want[12:15] and got[-1] == '0'
+	out = capsys.readouterr().out
+	assert '(file errors:0 + frame count errors:0)' in out and 'valid runs::' in out
+	assert os.path.isfile(tmp_path / 'eval_current.txt')
+
+
+def test_iou_per_annotator_length_and_malformed_boxes(engine):
+	"""The reference breaks out of the frame loop per annotator (retargetvid_eval.py:163-179): an annotator with a
+	shorter list is averaged over its own frames only.  A box with x2 < x1 is not an IoU in [0, 1]: loud error."""
+	from oracle import eval_oracle
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import retargetvid_eval as rev
+	rng = np.random.default_rng(11)
+
+	def boxes(n):
+		b = rng.integers(0, 600, (n, 4)).astype(np.int32)
+		b[:, 2:] = np.maximum(b[:, 2:], b[:, :2])
+		return b
+	method = {5: boxes(60), 9: boxes(33)}
+	annots = [{5: boxes(60), 9: boxes(40)}, {5: boxes(41), 9: boxes(40)}]       # annotator 2 stops early on video 5
+	fc = {5: 60, 9: 40}
+	vid_iou, _, order = rev.evaluate_arrays(engine.ctx, method, annots, fc)
+	for i, v in enumerate(order):
+		for u in range(2):
+			want = eval_oracle.video_iou([list(b) for b in method[v]], [list(b) for b in annots[u][v]], fc[v])
+			assert vid_iou[i][u] == want, (v, u)
+	bad = {5: method[5].copy(), 9: method[9]}
+	bad[5][3] = [400, 10, 100, 50]           # x2 < x1
+	with pytest.raises(_cabi.RvbError):
+		rev.evaluate_arrays(engine.ctx, bad, annots, fc)

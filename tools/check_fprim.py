@@ -1,4 +1,4 @@
-"""GPU check: the lattice-local Prim (fprim_kernel) against the all-pairs Prim (RVB_DENSE_PRIM=1) on bench clips:
+"""GPU check: the lattice-local Prim (fprim_kernel) against the all-pairs Prim (the default; RVB_FRONTIER_PRIM=1 selects the lattice-local one) on bench clips:
 boxes, centres, per-map records and filtered maps must be identical.  Prints the stage times and work counters.
 
     python tools/check_fprim.py [n_clips]
@@ -17,9 +17,9 @@ from retargetvid_b200.engine import CropEngine  # noqa: E402
 
 def run(vds, dense, want_filtered):
 	if dense:
-		os.environ['RVB_DENSE_PRIM'] = '1'
+		os.environ.pop('RVB_FRONTIER_PRIM', None)
 	else:
-		os.environ.pop('RVB_DENSE_PRIM', None)
+		os.environ['RVB_FRONTIER_PRIM'] = '1'
 	eng = CropEngine(0)
 	CP = svc.sc_init_crop_params()
 	eng.run(vds, CP, ['1:3', '3:1'], detail=True, want_filtered=want_filtered)
@@ -40,11 +40,15 @@ def main():
 	n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 	vds = [synth.make_clip(**sp) for sp in synth.config_clips(3, n_clips=n)]
 	out = {}
+	if '--frontier-only' in sys.argv:      # (for ncu captures)
+		res, dt, cyc, st = run(vds, False, False)
+		print('frontier call %.1f ms, stage ms %s, prim cycles %d, work %s' % (dt * 1e3, st, cyc[3], cyc[11:16]))
+		return 0
 	for dense in (True, False):
 		res, dt, cyc, st = run(vds, dense, True)
 		out[dense] = res
 		print('dense' if dense else 'frontier', 'call %.1f ms, stage ms (front, prim, back, all) %s' % (dt * 1e3, st))
-		print('  prim cycles %d, work [steps, stalls, far pair-vectors, near updates] %s' % (cyc[3], cyc[12:16]))
+		print('  prim cycles %d, work [steps, stalls, far pair-vectors, near updates, batches] %s' % (cyc[3], cyc[11:16]))
 	bad = 0
 	for i, (a, b) in enumerate(zip(out[True], out[False])):
 		ok = (np.array_equal(a.boxes, b.boxes) and np.array_equal(a.dx, b.dx) and np.array_equal(a.dy, b.dy)
