@@ -509,17 +509,55 @@ def gpu_arm(args, rank, world, local_rank):
 		torch.cuda.synchronize()
 		ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 		ei0.record(streams[0])
+		iou_k_ms = 0.0
 		for _ in range(args.steps):
 			ctx.iou_batch(ib)
+			iou_k_ms += ctx.last_iou_kernel_ms() / args.steps       # (synchronises: the calls do not overlap the host work)
 		ei1.record(streams[0])
 		torch.cuda.synchronize()
 		iou_ms = ei0.elapsed_time(ei1) / args.steps
 		iou_bytes = nfi * (16 + 16 * U)
 		iou = {'what': 'rvb_iou_batch_run (iou_kernel): %d frames x %d annotators per call, device-resident boxes, one call per step '
 						'(includes the per-call frame->video table upload)' % (nfi, U),
-				'ious_per_sec': nfi * U / (iou_ms / 1e3), 'ms_per_call': iou_ms, 'algorithmic_bytes_per_call': iou_bytes,
-				'achieved_gbs': iou_bytes / (iou_ms / 1e3) / 1e9}
+				'ious_per_sec': nfi * U / (iou_k_ms / 1e3), 'ms_per_call': iou_ms, 'kernel_ms_per_call': iou_k_ms,
+				'algorithmic_bytes_per_call': iou_bytes, 'achieved_gbs': iou_bytes / (iou_k_ms / 1e3) / 1e9,
+				'note': 'achieved_gbs / frac are for the kernel (CUDA events around its launch inside the library); ms_per_call adds the host-side '
+						'packing and upload of the per-video tables, which bounds back-to-back calls'}
 		del method, annot, acc
+
+	# the renderer's per-frame crop (smartVidCrop.py:1906-1912) on device-resident frames: pure data
+	# movement, rows of 360 bytes cut out of rows of 1920 bytes at an arbitrary byte offset
+	crop = None
+	if rank == 0:
+		nfr = 1000
+		frames_t = torch.randint(0, 256, (nfr, 360, 640, 3), dtype=torch.uint8, device='cuda')
+		bx = wl.dev_boxes[0][0, :nfr].cpu().numpy().copy() if not c5_main else None
+		if bx is not None and bx.shape[0] == nfr:
+			oh, ow = int(bx[0, 3] - bx[0, 1]), int(bx[0, 2] - bx[0, 0])
+			out_t = torch.empty((nfr, oh, ow, 3), dtype=torch.uint8, device='cuda')
+			lib = _cabi.load_library()
+
+			def crop_call():
+				_cabi.check(lib.rvb_crop_frames(ctx.handle, frames_t.data_ptr(), nfr, 360, 640, 3, bx.ctypes.data, oh, ow, out_t.data_ptr(), _cabi.RVB_MEM_DEVICE))
+			for _ in range(3):
+				crop_call()
+			torch.cuda.synchronize()
+			ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			ec0.record(streams[0])
+			for _ in range(args.steps):
+				crop_call()
+			ec1.record(streams[0])
+			torch.cuda.synchronize()
+			crop_ms = ec0.elapsed_time(ec1) / args.steps
+			f0 = 17
+			x1, y1, x2, y2 = (int(v) for v in bx[f0])
+			assert torch.equal(out_t[f0], frames_t[f0, y1:y2, x1:x2, :])
+			cbytes = 2 * nfr * oh * ow * 3
+			crop = {'what': 'rvb_crop_frames (crop_frames_kernel): %d device-resident 640x360x3 frames -> %dx%d crops along the 1:3 track of the step '
+							'(read + write of the cropped pixels; includes the per-call upload of the boxes)' % (nfr, ow, oh),
+					'ms_per_call': crop_ms, 'algorithmic_bytes_per_call': cbytes, 'achieved_gbs': cbytes / (crop_ms / 1e3) / 1e9}
+			del out_t
+		del frames_t
 
 	# BASELINE.json configs[0]: ONE 300-frame clip through the drop-in python entry point (host numpy maps in, boxes out)
 	c1 = None
@@ -657,11 +695,15 @@ def gpu_arm(args, rank, world, local_rank):
 			'single_clip': c1,
 			'prim_stage': prim,
 			'iou_stage': iou,
+			'crop_stage': crop,
 			'clocks': clocks,
 		}
 		if iou is not None:
 			iou['peak_gbs'] = peak
 			iou['frac'] = iou['achieved_gbs'] / peak
+		if crop is not None:
+			crop['peak_gbs'] = peak
+			crop['frac'] = crop['achieved_gbs'] / peak
 		if cpu_v is not None:
 			line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cpu_cores, 'kind': 'port', 'sample': cpu_desc}
 	if dist is not None:

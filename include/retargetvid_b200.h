@@ -71,7 +71,7 @@ typedef struct rvb_params {
 	double  foces_stab_s;
 	double  loess_w_secs;
 	double  lp_cutoff;
-	double  resize_factor;        /* 1.0, or any factor except 2.0 (OpenCV's INTER_AREA special case) */
+	double  resize_factor;        /* >= 1.0; exactly 2.0 with resize_type 1 takes OpenCV's INTER_AREA path like cv2.resize does */
 	double  t_cvrg;
 } rvb_params;
 
@@ -161,6 +161,9 @@ int rvb_ctx_last_map_kernel_ms(rvb_ctx *ctx, float *ms, int32_t *launches);
  * side on their own streams), 0, whole map pipeline incl. the joined side stream with the chains} */
 int rvb_ctx_last_stage_ms(rvb_ctx *ctx, float out[4]);
 
+/* CUDA-event time (ms) of the IoU kernel of the last rvb_iou_batch_run call (without the table upload around it) */
+int rvb_ctx_last_iou_kernel_ms(rvb_ctx *ctx, float *ms);
+
 /* profiling aid: when enabled, the map kernel accumulates SM cycles per phase (11 phases: load, threshold+compact,
  * core distances, Prim, argsort emulation, Cartesian tree, condensed-tree BFS, fall-out, EOM+labels, rebuild+closing,
  * results), summed over CTAs since the last call of this function */
@@ -180,6 +183,13 @@ int rvb_iou_batch_run(rvb_ctx *ctx, const rvb_iou_batch *b);
 /* exactly rounded mean of n IoU doubles from their exact sum (statistics.mean,
  * retargetvid_eval.py:193): acc = {lo, hi} in units of 2^-80 */
 double rvb_iou_mean_from_acc(const uint64_t acc[2], int64_t n);
+
+/* replaces the per-frame crop of sc_renderer (smartVidCrop.py:1906-1912): out[f] = frames[f][by1:by2, bx1:bx2, :].
+ * frames: uint8 [n_frames][h][w][channels] and out: uint8 [n_frames][out_h][out_w][channels], both in mem_space;
+ * boxes: HOST int32 [n_frames][4] = x1,y1,x2,y2 as rvb_crop_track_batch returns them; every box must measure
+ * out_w x out_h and lie inside the frame (RVB_ERR_INVALID otherwise). */
+int rvb_crop_frames(rvb_ctx *ctx, const uint8_t *frames, int32_t n_frames, int32_t h, int32_t w, int32_t channels,
+                    const int32_t *boxes, int32_t out_h, int32_t out_w, uint8_t *out, int32_t mem_space);
 
 /* stage-level entry points used by the parity tests (device work only) */
 /* sc_clustering_filt on one uint8 map in host memory -- smartVidCrop.py:1062-1161 */

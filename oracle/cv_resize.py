@@ -2,8 +2,9 @@
 (smartVidCrop.py:1078-1084, 1158, 1184) for uint8 single-channel images: INTER_LINEAR (OpenCV
 modules/imgproc/src/resize.cpp: float32 source coordinate, weights rounded to 1/2048, horizontal pass
 in int, vertical pass ((b*(S>>4))>>16, +2, >>2) with clipped rows) and INTER_NEAREST.  Checked against
-cv2 itself in tests/test_cpu_host.py.  Exact 2x down-scaling is not covered (OpenCV switches INTER_LINEAR to
-INTER_AREA there); neither preset uses it."""
+cv2 itself in tests/test_cpu_host.py.  For fx = fy = 1/2 OpenCV switches INTER_LINEAR to INTER_AREA
+(resize.cpp: is_area_fast && iscale == 2): resize_area2_u8 restates that path (full 2x2 cells (sum + 2) >> 2, the
+partial cells of an odd size saturate_cast<uchar>(float(sum) / count), i.e. round half to even)."""
 import numpy as np
 
 
@@ -59,3 +60,22 @@ def resize_nearest_u8(src, fx, fy):
 	xs = np.minimum(np.floor(np.arange(dw) * (1.0 / fx)).astype(np.int64), W - 1)
 	ys = np.minimum(np.floor(np.arange(dh) * (1.0 / fy)).astype(np.int64), H - 1)
 	return src[ys][:, xs]
+
+
+def resize_area2_u8(src):
+	"""cv2.resize(src, None, fx=0.5, fy=0.5, INTER_LINEAR) -> INTER_AREA fast path (resizeAreaFast_, scale 2)."""
+	H, W = src.shape
+	dw, dh = cv_round(W * 0.5), cv_round(H * 0.5)
+	s = src.astype(np.int64)
+	out = np.zeros((dh, dw), dtype=np.uint8)
+	for y in range(dh):
+		for x in range(dw):
+			y0, x0 = 2 * y, 2 * x
+			if y0 >= H or x0 >= W:
+				continue
+			blk = s[y0:min(y0 + 2, H), x0:min(x0 + 2, W)]
+			if blk.size == 4:
+				out[y, x] = (int(blk.sum()) + 2) >> 2
+			else:
+				out[y, x] = cv_round(np.float32(blk.sum()) / np.float32(blk.size))
+	return out

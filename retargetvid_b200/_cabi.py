@@ -30,7 +30,7 @@ RVB_MAPS_F32_NHW = 2
 EXPORTS = ['rvb_version', 'rvb_last_error', 'rvb_ctx_create', 'rvb_ctx_destroy', 'rvb_ctx_set_stream',
 		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_ctx_last_stage_ms', 'rvb_params_default',
 		'rvb_crop_track_batch', 'rvb_iou_batch_run', 'rvb_iou_mean_from_acc', 'rvb_debug_cluster_labels',
-		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles']
+		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms']
 
 
 class RvbError(RuntimeError):
@@ -108,6 +108,9 @@ def load_library():
 											C.c_void_p, C.POINTER(C.c_int32)]
 	lib.rvb_debug_smooth_series.argtypes = [C.c_void_p, C.POINTER(rvb_params), C.c_void_p, C.c_int32, C.c_double,
 											C.c_void_p, C.c_void_p]
+	lib.rvb_ctx_last_iou_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+	lib.rvb_crop_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+									C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
 	_lib = lib
 	return lib
 
@@ -192,6 +195,11 @@ class Context(object):
 		check(self.lib.rvb_ctx_last_map_kernel_ms(self.handle, C.byref(ms), C.byref(n)))
 		return float(ms.value), int(n.value)
 
+	def last_iou_kernel_ms(self):
+		ms = C.c_float()
+		check(self.lib.rvb_ctx_last_iou_kernel_ms(self.handle, C.byref(ms)))
+		return float(ms.value)
+
 	def phase_cycles(self, enable=True):
 		out = (C.c_uint64 * 16)()
 		check(self.lib.rvb_ctx_phase_cycles(self.handle, 1 if enable else 0, out))
@@ -206,6 +214,17 @@ class Context(object):
 	def iou_mean_from_acc(self, lo, hi, n):
 		a = (C.c_uint64 * 2)(int(lo), int(hi))
 		return float(self.lib.rvb_iou_mean_from_acc(a, int(n)))
+
+	def crop_frames(self, frames, boxes):
+		"""frames: uint8 [F, H, W, C] numpy array; boxes: [F, 4] x1,y1,x2,y2 of one size.  Returns uint8 [F, h, w, C]
+		(the per-frame crop of the reference's renderer, smartVidCrop.py:1906-1912)."""
+		fr = np.ascontiguousarray(frames, dtype=np.uint8)
+		bb = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+		F, H, W, Cn = fr.shape
+		ow, oh = int(bb[0, 2] - bb[0, 0]), int(bb[0, 3] - bb[0, 1])
+		out = np.empty((F, oh, ow, Cn), dtype=np.uint8)
+		check(self.lib.rvb_crop_frames(self.handle, fr.ctypes.data, F, H, W, Cn, bb.ctypes.data, oh, ow, out.ctypes.data, RVB_MEM_HOST))
+		return out
 
 	def debug_cluster_labels(self, params, map_hw):
 		m = np.ascontiguousarray(map_hw, dtype=np.uint8)

@@ -111,7 +111,7 @@ struct MapArgs {
 	int32_t *labels_dbg;       // optional: labels of the single map being debugged
 	unsigned long long *phase_cycles;  // optional [16]: SM cycles spent per phase, summed over CTAs (profiling aid)
 	// resize_factor != 1 (smartVidCrop.py:1078-1084,1158,1184): cluster a down-scaled copy, scale the result back
-	int resize_on, resize_type;    // type 1: INTER_LINEAR, 3: INTER_NEAREST (down-scaling only)
+	int resize_on, resize_type;    // type 1: INTER_LINEAR, 3: INTER_NEAREST, 4: INTER_AREA by exactly 2 (what OpenCV makes of INTER_LINEAR at fx = 1/2)
 	int Hs, Ws, WSs;               // small size and its shared-memory row stride
 	double factor;
 	const int16_t *rz;             // coefficient tables, offsets below (int16 entries)
@@ -1035,6 +1035,25 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 			__syncthreads();
 			if (a.resize_type == 1) {
 				cv_resize_linear_u8(map8, H, W, WPS, small8, a.Hs, a.Ws, a.WSs, a.rz + a.rz_dx, a.rz + a.rz_dy, NT);
+			} else if (a.resize_type == 4) {
+				// resizeAreaFast_ (OpenCV resize.cpp), scale 2: full cells (sum + 2) >> 2; the partial cells of an odd size
+				// saturate_cast<uchar>(float(sum) / count) = round half to even
+				for (int i = tid; i < a.Hs * a.Ws; i += NT) {
+					const int y = i / a.Ws, x = i - y * a.Ws;
+					const int y0 = 2 * y, x0 = 2 * x;
+					uint32_t v = 0u;
+					if (y0 < H && x0 < W) {
+						const bool y1 = (y0 + 1) < H, x1 = (x0 + 1) < W;
+						uint32_t sum = map8[y0 * WPS + x0];
+						if (x1) sum += map8[y0 * WPS + x0 + 1];
+						if (y1) sum += map8[(y0 + 1) * WPS + x0];
+						if (x1 && y1) sum += map8[(y0 + 1) * WPS + x0 + 1];
+						if (x1 && y1) v = (sum + 2u) >> 2;
+						else if (x1 || y1) v = (sum >> 1) + ((sum & 1u) & ((sum >> 1) & 1u));   // sum / 2, half to even
+						else v = sum;
+					}
+					small8[y * a.WSs + x] = (uint8_t)v;
+				}
 			} else {
 				const int16_t *nx = a.rz + a.rz_nx, *ny = a.rz + a.rz_ny;
 				for (int i = tid; i < a.Hs * a.Ws; i += NT) {

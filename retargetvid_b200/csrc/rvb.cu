@@ -92,10 +92,13 @@ struct rvb_ctx {
 	cudaStream_t cls_stream[kSplitClasses] = {};   // one per size class: Prim + back of the classes run side by side
 	cudaEvent_t ev_cls[kSplitClasses] = {};
 	cudaEvent_t ev_cls_fork = nullptr;
-	bool serial_classes = false;          // RVB_SERIAL_CLASSES=1: the classes one after the other on the main stream
+	bool serial_classes = true;           // the size classes one after the other on the main stream (default: measured faster
+	                                      // with several batches in flight); RVB_FAN_CLASSES=1: each class on its own stream
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_map0 = nullptr, ev_map1 = nullptr, ev_stage = nullptr;
+	cudaEvent_t ev_iou0 = nullptr, ev_iou1 = nullptr;
+	bool iou_timed = false;
 	cudaEvent_t ev_st[3] = {nullptr, nullptr, nullptr};   // split pipeline, main stream: after front / Prim / back of set 0
 	bool stages_timed = false;
 	bool stage_busy = false;
@@ -373,6 +376,8 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	c->n_sm = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
+	CU(cudaEventCreate(&c->ev_iou0));
+	CU(cudaEventCreate(&c->ev_iou1));
 	CU(cudaEventCreate(&c->ev_map0));
 	CU(cudaEventCreate(&c->ev_map1));
 	for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&c->ev_st[i]));
@@ -394,8 +399,8 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 	}
 	CU(cudaEventCreateWithFlags(&c->ev_cls_fork, cudaEventDisableTiming));
 	{
-		const char *e = getenv("RVB_SERIAL_CLASSES");
-		c->serial_classes = (e && e[0] == '1');
+		const char *e = getenv("RVB_FAN_CLASSES");
+		c->serial_classes = !(e && e[0] == '1');
 	}
 	CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -453,6 +458,8 @@ extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
 	for (DevBuf *b : bufs) b->release();
 	c->stage.release();
 	c->stage_out.release();
+	if (c->ev_iou0) cudaEventDestroy(c->ev_iou0);
+	if (c->ev_iou1) cudaEventDestroy(c->ev_iou1);
 	if (c->ev_map0) cudaEventDestroy(c->ev_map0);
 	if (c->ev_map1) cudaEventDestroy(c->ev_map1);
 	for (int i = 0; i < 3; ++i) if (c->ev_st[i]) cudaEventDestroy(c->ev_st[i]);
@@ -493,6 +500,14 @@ extern "C" int rvb_ctx_last_map_kernel_ms(rvb_ctx *c, float *ms, int32_t *launch
 	CU(cudaEventElapsedTime(&t, c->ev_map0, c->ev_map1));
 	if (ms) *ms = t;
 	if (launches) *launches = c->map_launches;
+	return RVB_OK;
+}
+
+extern "C" int rvb_ctx_last_iou_kernel_ms(rvb_ctx *c, float *ms) {
+	if (!c || !ms) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (!c->iou_timed) return fail(RVB_ERR_INVALID, "no iou_batch call has run on this context");
+	CU(cudaEventSynchronize(c->ev_iou1));
+	CU(cudaEventElapsedTime(ms, c->ev_iou0, c->ev_iou1));
 	return RVB_OK;
 }
 
@@ -628,8 +643,8 @@ struct Staging {  // packs the small per-call arrays into one pinned block -> on
 extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_batch *b) {
 	if (!c || !p || !b) return fail(RVB_ERR_INVALID, "NULL argument");
 	if (p->resize_factor != 1.0) {
-		if (!(p->resize_factor > 1.0) || p->resize_factor == 2.0)
-			return fail(RVB_ERR_UNSUPPORTED, "resize_factor=%g (must be 1 or > 1 and not 2: OpenCV resizes by exactly 2 with INTER_AREA)", p->resize_factor);
+		if (!(p->resize_factor > 1.0))
+			return fail(RVB_ERR_UNSUPPORTED, "resize_factor=%g (up-scaling before the clustering is not built)", p->resize_factor);
 		if (p->resize_type != 1 && p->resize_type != 3)
 			return fail(RVB_ERR_UNSUPPORTED, "resize_type=%d: only bilinear (1) and nearest (3) are built", p->resize_type);
 	}
@@ -707,6 +722,10 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		if (shots[d.shot_offset + cl.n_shots - 1].f1 != cl.n_frames - 1)
 			return fail(RVB_ERR_INVALID, "clip %d: last shot must end at the last frame", i);
 		// cut-adjacent blend (smartVidCrop.py:2369-2373): map k+1 <- (map k+1 + filtered map k) / 2
+		// (when every filtered map is kept -- returned to the caller, or sampled by focus stability -- the slots are the map
+		// indices, so the maps come back with one strided copy)
+		if (keep_all_maps)
+			for (int k = 0; k < cl.n_maps; ++k) store[d.map_offset + k] = d.map_offset + k;
 		if (p->clust_filt) {
 			for (int k = 0; k < cl.n_maps - 2; ++k) {
 				const bool hit = (k >= 1 && is_cut[k - 1]) || is_cut[k] || is_cut[k + 1];
@@ -718,8 +737,6 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 				}
 			}
 		}
-		if (keep_all_maps)
-			for (int k = 0; k < cl.n_maps; ++k) if (store[d.map_offset + k] < 0) store[d.map_offset + k] = n_slots++;
 		for (int r = 0; r < R; ++r) {
 			int fin[3];
 			calc_dest_size(cl.w_orig, cl.h_orig, b->ratio_w[r], b->ratio_h[r], fin);
@@ -742,6 +759,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		}
 		clip_coef[i] = ci;
 	}
+	if (keep_all_maps) n_slots = NM;
 	if (scratch_doubles > 0x7fffffffLL) return fail(RVB_ERR_INVALID, "batch too large (scratch)");
 	// Monolithic path: every map that does not wait for a predecessor is a work item; a chain is walked by the CTA that
 	// took its first map (chain_next), so there are no waves and no inter-CTA waits.
@@ -829,6 +847,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_minfo = sg.add(nullptr, (size_t)NM * 4 * sizeof(int));
 	const size_t o_empty = sg.add(nullptr, (size_t)NM);
 	const size_t o_minmax = sg.add(nullptr, (size_t)NS * 4 * sizeof(double));
+	const size_t o_nf = sg.add(nullptr, (size_t)((b->centres_nf && host) ? 2 * NM : 0) * sizeof(double));
 	const size_t meta_bytes = sg.bytes.size();
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
 	if (c->stage.ensure(meta_bytes)) return RVB_ERR_CUDA;
@@ -934,7 +953,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.border_prof = nullptr;
 	a.cvrg_cfg = p->exit_on_low_cvrg ? (const int *)(M + o_cvrg) : nullptr;
 	a.n_ratios = R; a.labels_dbg = nullptr;
-	a.resize_on = rzs.on; a.resize_type = p->resize_type; a.Hs = rzs.Hs; a.Ws = rzs.Ws; a.WSs = rzs.WSs; a.factor = p->resize_factor;
+	a.resize_on = rzs.on; a.resize_type = (p->resize_type == 1 && p->resize_factor == 2.0) ? 4 : p->resize_type; a.Hs = rzs.Hs; a.Ws = rzs.Ws; a.WSs = rzs.WSs; a.factor = p->resize_factor;
 	a.rz = (const int16_t *)(M + o_rz); a.rz_dx = rzs.dx; a.rz_dy = rzs.dy; a.rz_ux = rzs.ux; a.rz_uy = rzs.uy; a.rz_nx = rzs.nx; a.rz_ny = rzs.ny;
 	a.phase_cycles = c->phase_on ? (unsigned long long *)c->phase.p : nullptr;
 	a.t_threshold = p->t_threshold; a.clust_filt = p->clust_filt; a.mcs = p->hdbscan_min;
@@ -966,13 +985,23 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 			// per CTA grows with the capacity, so smaller classes keep more maps in flight per SM): a map that does not
 			// fit is appended to the next class's list by the kernel itself (no host round trip)
 			auto launch_mono = [&](int k_first, cudaStream_t stream) -> int {
-				for (int k = k_first; k < 5; ++k) {
+				// the largest class whose shared-memory layout fits this process size (a large down-scaled copy, or a process
+				// size above 140 x 250, can push the 8192-point class over the per-CTA limit)
+				static const int kCaps[5] = {1536, 2048, 3072, 4096, 8192};
+				int k_last = -1;
+				for (int k = 0; k < 5; ++k)
+					if (make_layout(kCaps[k], H, WPS, W, mcs, small_bytes).total <= (kCaps[k] > 4096 ? kMaxDynSmem : 200 * 1024)) k_last = k;
+				if (k_last < k_first) {
+					if (k_first > 0) return RVB_OK;      // (only a fallback for overflow was asked for)
+					return fail(RVB_ERR_UNSUPPORTED, "process size %dx%d does not fit the shared memory of any capacity class", H, W);
+				}
+				for (int k = k_first; k <= k_last; ++k) {
 					a.list = (k == 0) ? (const int *)(M + o_work) : ovf[k - 1];
 					a.head = cnt + 2 * k;
 					a.list_len = cnt + 2 * k + 1;
 					// anything larger than the last class is flagged RVB_ERR_CAPACITY by the kernel
-					a.ovf_list = (k < 4) ? ovf[k] : nullptr;
-					a.ovf_len = (k < 4) ? cnt + 2 * k + 3 : nullptr;
+					a.ovf_list = (k < k_last) ? ovf[k] : nullptr;
+					a.ovf_len = (k < k_last) ? cnt + 2 * k + 3 : nullptr;
 					int rc = RVB_OK;
 					const int nwk = (k == 0) ? nw : nw + n_split;   // later classes also receive overflow
 					if (k == 0) rc = launch_map<256, 6>(c, a, H, W, WPS, occupancy_grid<256, 6>(c, make_layout(1536, H, WPS, W, mcs, small_bytes).total, nwk), stream);
@@ -1144,8 +1173,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	fill_centres_kernel<<<(nc * 32 + 127) / 128, 128, 0, st>>>(d_clips, nc, d_shots, d_mo, d_dx, d_dy, d_empty, d_status);
 	double *d_jumps = (double *)(M + o_jumps);
 	if (b->centres_nf) {  // dxnf, dynf: the centres before focus stability (smartVidCrop.py:2450-2451)
-		const cudaMemcpyKind knf = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-		CU(cudaMemcpyAsync(b->centres_nf, d_dx, (size_t)2 * NM * sizeof(double), knf, st));
+		// (host buffers: kept on the device until the results are copied out, so that the call does not block here)
+		CU(cudaMemcpyAsync(host ? (void *)(M + o_nf) : (void *)b->centres_nf, d_dx, (size_t)2 * NM * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	}
 	if (p->focus_stability) {
 		focus_jumps_kernel<<<(NM + 127) / 128, 128, 0, st>>>(d_clips, (const int *)(M + o_mclip), NM, d_dx, d_dy, (const uint8_t *)c->filt.p,
@@ -1153,22 +1182,21 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		focus_apply_kernel<<<(nc + 63) / 64, 64, 0, st>>>(d_clips, nc, d_jumps, p->foces_stab_t, p->foces_stab_s, p->skip, d_dx, d_dy);
 		c->launches += 2;
 	}
-	if (b->centres_nf) {
-		const cudaMemcpyKind knf = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-		if (p->focus_stability) CU(cudaMemcpyAsync(b->centres_nf + 2 * (size_t)NM, d_jumps, (size_t)NM * sizeof(double), knf, st));
-	}
+	if (b->centres_nf && !host && p->focus_stability)
+		CU(cudaMemcpyAsync(b->centres_nf + 2 * (size_t)NM, d_jumps, (size_t)NM * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	const int sp_doubles = (int)std::min<long long>(max_spline_doubles, 6144);   // up to 48 KB of shared memory per warp
 	spline_setup_kernel<<<NS, 32, (size_t)sp_doubles * sizeof(double), st>>>(d_shots, NS, d_ti, d_dx, d_dy, d_scratch, sp_doubles);
 	interp_eval_kernel<<<(NF + 255) / 256, 256, 0, st>>>(d_shots, d_fshot, NF, d_ti, d_dx, d_dy, d_scratch, d_dxi, d_dyi);
 	const int lp_doubles = (int)std::min<long long>(max_lp_doubles, 6144);
 	double *d_minmax = (double *)(M + o_minmax);
 	lowpass_kernel<<<2 * NS, 32, (size_t)lp_doubles * sizeof(double), st>>>(d_shots, NS, d_clips, (const FilterCoef *)(M + o_coefs),
-													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt, lp_doubles, d_minmax);
+													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt, lp_doubles, d_minmax,
+													   p->loess_filt, p->loess_w_secs, p->loess_degree);
 	{
 		const long long warps = 2LL * NF;
 		const int blocks = (int)((warps * 32 + 255) / 256);
 		smooth_kernel<<<blocks, 256, 0, st>>>(d_shots, d_fshot, NF, d_clips, d_dxl, d_dyl, d_dxs, d_dys, p->loess_filt,
-											  p->loess_w_secs, p->loess_degree, d_minmax);
+											  p->loess_w_secs, p->loess_degree, d_minmax, d_scratch);
 	}
 	int32_t *d_dims = (int32_t *)(M + o_dims);
 	boxes_kernel<<<(int)(((long long)NF * R + 255) / 256), 256, 0, st>>>(d_clips, d_fclip, NF, R, (const int *)(M + o_final),
@@ -1179,33 +1207,75 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	c->launches += 7;
 
 	// ---- results -----------------------------------------------------------------------------------
+	// Host buffers: a copy into pageable memory is staged by the driver and blocks the calling thread, once per array.
+	// So every output whose destination is not page-locked goes through one pinned block of the context (asynchronous
+	// copies, one synchronisation at the end, then plain memcpys); page-locked destinations are written directly.
+	struct Pending { void *dst; size_t off, n; size_t rows, w, dpitch; };
+	std::vector<Pending> pend;
+	size_t stage_bytes = 0;
+	auto pinned = [&](const void *ptr) -> bool {
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+		return at.type == cudaMemoryTypeHost;
+	};
+	struct Out { void *dst; const void *src; size_t n; size_t spitch, w, rows, dpitch; };   // rows == 0: flat copy of n bytes
+	std::vector<Out> outs;
 	const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-	if (host) CU(cudaMemcpyAsync(b->boxes, d_boxes, (size_t)R * NF * 4 * sizeof(int32_t), kind, st));
-	if (b->centres) CU(cudaMemcpyAsync(b->centres, d_dx, (size_t)2 * NM * sizeof(double), kind, st));
-	if (b->empty) CU(cudaMemcpyAsync(b->empty, d_empty, (size_t)NM, kind, st));
-	if (b->series) CU(cudaMemcpyAsync(b->series, d_ser, (size_t)6 * NF * sizeof(double), kind, st));
-	if (b->map_scores) CU(cudaMemcpyAsync(b->map_scores, d_mscore, (size_t)NM * sizeof(double), kind, st));
-	if (b->clip_scores) CU(cudaMemcpyAsync(b->clip_scores, d_cscore, (size_t)nc * (1 + R) * sizeof(double), kind, st));
-	if (b->clip_dims) CU(cudaMemcpyAsync(b->clip_dims, d_dims, (size_t)nc * R * 9 * sizeof(int), kind, st));
-	if (b->clip_status) CU(cudaMemcpyAsync(b->clip_status, d_status, (size_t)nc * sizeof(int), kind, st));
-	if (b->map_info) {
-		// n_points, n_clusters, kept_points, flags are 4 consecutive ints inside MapOut
-		CU(cudaMemcpy2DAsync(b->map_info, 4 * sizeof(int), (const uint8_t *)d_mo + offsetof(MapOut, n_points), sizeof(MapOut),
-							 4 * sizeof(int), NM, kind, st));
+	if (host) outs.push_back({b->boxes, d_boxes, (size_t)R * NF * 4 * sizeof(int32_t), 0, 0, 0, 0});
+	if (b->centres) outs.push_back({b->centres, d_dx, (size_t)2 * NM * sizeof(double), 0, 0, 0, 0});
+	if (b->centres_nf && host) {
+		outs.push_back({b->centres_nf, M + o_nf, (size_t)2 * NM * sizeof(double), 0, 0, 0, 0});
+		if (p->focus_stability) outs.push_back({b->centres_nf + 2 * (size_t)NM, d_jumps, (size_t)NM * sizeof(double), 0, 0, 0, 0});
 	}
+	if (b->empty) outs.push_back({b->empty, d_empty, (size_t)NM, 0, 0, 0, 0});
+	if (b->series) outs.push_back({b->series, d_ser, (size_t)6 * NF * sizeof(double), 0, 0, 0, 0});
+	if (b->map_scores) outs.push_back({b->map_scores, d_mscore, (size_t)NM * sizeof(double), 0, 0, 0, 0});
+	if (b->clip_scores) outs.push_back({b->clip_scores, d_cscore, (size_t)nc * (1 + R) * sizeof(double), 0, 0, 0, 0});
+	if (b->clip_dims) outs.push_back({b->clip_dims, d_dims, (size_t)nc * R * 9 * sizeof(int), 0, 0, 0, 0});
+	if (b->clip_status) outs.push_back({b->clip_status, d_status, (size_t)nc * sizeof(int), 0, 0, 0, 0});
+	// n_points, n_clusters, kept_points, flags are 4 consecutive ints inside MapOut
+	if (b->map_info) outs.push_back({b->map_info, (const uint8_t *)d_mo + offsetof(MapOut, n_points), 0, sizeof(MapOut), 4 * sizeof(int), (size_t)NM, 4 * sizeof(int)});
 	if (want_filtered) {
 		const int so = b->row_stride_out > 0 ? b->row_stride_out : WPS;
 		if (so < W) return fail(RVB_ERR_INVALID, "row_stride_out=%d", so);
-		// slots were handed out in map order when filtered maps are requested only if no blend slot came first,
-		// so copy map by map through the slot table
-		for (int m = 0; m < NM; ++m)
-			CU(cudaMemcpy2DAsync(b->filtered_maps + (size_t)m * H * so, so, (const uint8_t *)c->filt.p + (size_t)store[m] * H * WPS,
-								 WPS, W, H, kind, st));
+		// slot m holds map m: all rows of all maps in one strided copy
+		outs.push_back({b->filtered_maps, c->filt.p, 0, (size_t)WPS, (size_t)W, (size_t)NM * H, (size_t)so});
+	}
+	if (host) {
+		for (const Out &o : outs) {
+			if (pinned(o.dst)) continue;
+			stage_bytes = (stage_bytes + 255) / 256 * 256;
+			stage_bytes += o.rows ? o.rows * o.w : o.n;
+		}
+		if (stage_bytes && c->stage_out.ensure(stage_bytes)) return RVB_ERR_CUDA;
+	}
+	{
+		size_t off = 0;
+		for (const Out &o : outs) {
+			const bool direct = !host || pinned(o.dst);
+			uint8_t *dst = (uint8_t *)o.dst;
+			size_t dpitch = o.dpitch;
+			if (!direct) {
+				off = (off + 255) / 256 * 256;
+				dst = (uint8_t *)c->stage_out.p + off;
+				dpitch = o.w;
+				pend.push_back({o.dst, off, o.n, o.rows, o.w, o.dpitch});
+				off += o.rows ? o.rows * o.w : o.n;
+			}
+			if (o.rows) CU(cudaMemcpy2DAsync(dst, dpitch, o.src, o.spitch, o.w, o.rows, kind, st));
+			else CU(cudaMemcpyAsync(dst, o.src, o.n, kind, st));
+		}
 	}
 	if (host) {
 		std::vector<int> status(nc);
 		CU(cudaMemcpyAsync(status.data(), d_status, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
+		for (const Pending &q : pend) {
+			const uint8_t *src = (const uint8_t *)c->stage_out.p + q.off;
+			if (q.rows == 0) memcpy(q.dst, src, q.n);
+			else if (q.dpitch == q.w) memcpy(q.dst, src, q.rows * q.w);
+			else for (size_t r = 0; r < q.rows; ++r) memcpy((uint8_t *)q.dst + r * q.dpitch, src + r * q.w, q.w);
+		}
 		for (int i = 0; i < nc; ++i)
 			if (status[i] != RVB_OK)
 				return fail(status[i], "clip %d: %s", i,
@@ -1275,9 +1345,12 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	CU(cudaMemsetAsync(d_acc, 0, (size_t)V * U * 2 * sizeof(uint64_t), st));
 	int *d_bad = (int *)(M + o_bad);
 	CU(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+	CU(cudaEventRecord(c->ev_iou0, st));
 	iou_kernel<<<dim3((unsigned)V, (unsigned)chunks), 256, 0, st>>>(d_method, d_annot, (const int *)(M + o_first),
 															(const int *)(M + o_ne), NF, U, d_fiou, d_acc, d_bad);
 	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->ev_iou1, st));
+	c->iou_timed = true;
 	c->launches += 1;
 	const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
 	CU(cudaMemcpyAsync(b->acc, d_acc, (size_t)V * U * 2 * sizeof(uint64_t), kind, st));
@@ -1330,6 +1403,56 @@ extern "C" double rvb_iou_mean_from_acc(const uint64_t acc[2], int64_t n) {
 	for (int i = top - 54; i >= 0 && !rest; --i) rest = bit(i) != 0;
 	if (guard && (rest || (mant & 1))) mant += 1;  // may carry to 2^53: ldexp handles it
 	return ldexp((double)mant, top - 52 - 64 - kIouFracBits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// renderer crop
+// ---------------------------------------------------------------------------------------------
+extern "C" int rvb_crop_frames(rvb_ctx *c, const uint8_t *frames, int32_t n_frames, int32_t h, int32_t w, int32_t channels,
+							   const int32_t *boxes, int32_t out_h, int32_t out_w, uint8_t *out, int32_t mem_space) {
+	if (!c || !frames || !boxes || !out) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (n_frames < 1 || h < 1 || w < 1 || channels < 1 || channels > 4 || out_h < 1 || out_w < 1 || out_h > h || out_w > w)
+		return fail(RVB_ERR_INVALID, "bad geometry: %d frames of %dx%dx%d -> %dx%d", n_frames, h, w, channels, out_h, out_w);
+	for (int f = 0; f < n_frames; ++f) {
+		const int32_t *b = boxes + (size_t)f * 4;
+		if (b[2] - b[0] != out_w || b[3] - b[1] != out_h || b[0] < 0 || b[1] < 0 || b[2] > w || b[3] > h)
+			return fail(RVB_ERR_INVALID, "frame %d: box %d,%d,%d,%d is not a %dx%d window inside %dx%d", f, b[0], b[1], b[2], b[3], out_w, out_h, w, h);
+	}
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const bool host = mem_space == RVB_MEM_HOST;
+	const size_t in_bytes = (size_t)n_frames * h * w * channels, out_bytes = (size_t)n_frames * out_h * out_w * channels;
+	const size_t box_bytes = (size_t)n_frames * 4 * sizeof(int32_t);
+	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
+	if (c->stage.ensure(box_bytes) || c->misc.ensure(box_bytes + 256)) return RVB_ERR_CUDA;
+	memcpy(c->stage.p, boxes, box_bytes);
+	CU(cudaMemcpyAsync(c->misc.p, c->stage.p, box_bytes, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->ev_stage, st));
+	c->stage_busy = true;
+	const uint8_t *d_in = frames;
+	uint8_t *d_out = out;
+	if (host) {
+		if (c->maps_in.ensure(in_bytes) || c->filt.ensure(out_bytes)) return RVB_ERR_CUDA;
+		CU(cudaMemcpyAsync(c->maps_in.p, frames, in_bytes, cudaMemcpyHostToDevice, st));
+		d_in = (const uint8_t *)c->maps_in.p;
+		d_out = (uint8_t *)c->filt.p;
+	}
+	const long long row_bytes = (long long)out_w * channels;
+	const bool al4 = ((uintptr_t)d_out & 7) == 0;
+	const int vec = (al4 && row_bytes % 8 == 0) ? 8 : (al4 && row_bytes % 4 == 0) ? 4 : 1;
+	const long long total = (long long)n_frames * out_h * (row_bytes / vec);
+	const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->n_sm * 32);
+	const int32_t *d_boxes = (const int32_t *)c->misc.p;
+	if (vec == 8) crop_frames_kernel<8><<<blocks, 256, 0, st>>>(d_in, n_frames, h, w, channels, d_boxes, out_h, out_w, d_out);
+	else if (vec == 4) crop_frames_kernel<4><<<blocks, 256, 0, st>>>(d_in, n_frames, h, w, channels, d_boxes, out_h, out_w, d_out);
+	else crop_frames_kernel<1><<<blocks, 256, 0, st>>>(d_in, n_frames, h, w, channels, d_boxes, out_h, out_w, d_out);
+	CU(cudaGetLastError());
+	c->launches += 1;
+	if (host) {
+		CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+	}
+	return RVB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1418,11 +1541,12 @@ extern "C" int rvb_debug_smooth_series(rvb_ctx *c, const rvb_params *p, const do
 	const int dbg_lp_doubles = std::min(n + 6 * (RVB_MAX_LP_ORDER + 1), 6144);
 	lowpass_kernel<<<2, 32, (size_t)dbg_lp_doubles * sizeof(double), st>>>((const ShotDev *)(D + o_sh), 1, (const ClipDev *)(D + o_cl), (const FilterCoef *)(D + o_fc),
 									  (const int *)(D + o_cc), (const double *)(D + o_x), (const double *)(D + o_y),
-									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt, dbg_lp_doubles, (double *)(D + o_mm));
+									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt, dbg_lp_doubles, (double *)(D + o_mm),
+									  p->loess_filt, p->loess_w_secs, p->loess_degree);
 	const int blocks = (int)((2LL * n * 32 + 255) / 256);
 	smooth_kernel<<<blocks, 256, 0, st>>>((const ShotDev *)(D + o_sh), (const int *)(D + o_fs), n, (const ClipDev *)(D + o_cl),
 										  (const double *)(D + o_xl), (const double *)(D + o_yl), (double *)(D + o_xs),
-										  (double *)(D + o_ys), p->loess_filt, p->loess_w_secs, p->loess_degree, (const double *)(D + o_mm));
+										  (double *)(D + o_ys), p->loess_filt, p->loess_w_secs, p->loess_degree, (const double *)(D + o_mm), (const double *)(D + o_scr));
 	CU(cudaGetLastError());
 	c->launches += 2;
 	if (lowpassed_out) CU(cudaMemcpyAsync(lowpassed_out, D + o_xl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));

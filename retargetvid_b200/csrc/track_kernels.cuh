@@ -249,12 +249,14 @@ __global__ void __launch_bounds__(32) spline_setup_kernel(const ShotDev *shots, 
 	}
 	__syncwarp();
 	if (lane == 0) {
-		// Gaussian elimination without pivoting (the collocation matrix is totally positive)
+		// Gaussian elimination without pivoting (the collocation matrix is totally positive).  One division per row: the
+		// reciprocal of the pivot is kept in the (dead) sub-diagonal slot band[i][0] for the back substitution.
 		for (int i = 0; i < n; ++i) {
-			const double piv = band[i * 5 + 2];
+			const double inv = 1.0 / band[i * 5 + 2];
+			band[i * 5 + 0] = inv;
 			for (int r = i + 1; r <= min(n - 1, i + 2); ++r) {
 				const int o = i - r + 2;  // column i in row r
-				const double f = band[r * 5 + o] / piv;
+				const double f = band[r * 5 + o] * inv;
 				if (f == 0.0) continue;
 				for (int c = i; c <= min(n - 1, i + 2); ++c) {
 					const int oi = c - i + 2, orr = c - r + 2;
@@ -270,8 +272,8 @@ __global__ void __launch_bounds__(32) spline_setup_kernel(const ShotDev *shots, 
 				sx -= band[i * 5 + (c - i + 2)] * cx[c];
 				sy -= band[i * 5 + (c - i + 2)] * cy[c];
 			}
-			cx[i] = sx / band[i * 5 + 2];
-			cy[i] = sy / band[i * 5 + 2];
+			cx[i] = sx * band[i * 5 + 0];
+			cy[i] = sy * band[i * 5 + 0];
 		}
 	}
 	__syncwarp();
@@ -344,21 +346,33 @@ __device__ __forceinline__ void filtfilt_inplace(const FilterCoef &fc, double *b
 		z[M - 1] = __dsub_rn(__dmul_rn(x, b[M]), __dmul_rn(y, a[M]));
 		return y;
 	};
+	// (the next sample is loaded before the current one enters the serial chain)
 	const double e0 = buf[0];
 #pragma unroll
 	for (int i = 0; i < M; ++i) z[i] = zi[i] * e0;
-	for (int i = 0; i < ne; ++i) buf[i] = step(buf[i]);
+	double xn = e0;
+	for (int i = 0; i < ne; ++i) {
+		const double xc = xn;
+		if (i + 1 < ne) xn = buf[i + 1];
+		buf[i] = step(xc);
+	}
 	const double y0 = buf[ne - 1];
 #pragma unroll
 	for (int i = 0; i < M; ++i) z[i] = zi[i] * y0;
-	for (int i = ne - 1; i >= 0; --i) buf[i] = step(buf[i]);
+	xn = y0;
+	for (int i = ne - 1; i >= 0; --i) {
+		const double xc = xn;
+		if (i > 0) xn = buf[i - 1];
+		buf[i] = step(xc);
+	}
 }
 
 // also leaves min / max of the low-passed series of every (shot, axis) in shot_minmax[(shot * 2 + axis) * 2 + {0, 1}]:
 // the LOESS stage normalises by them (pyloess.py:16-24) and would otherwise rescan the shot for every output frame
 __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n_shots, const ClipDev *clips, const FilterCoef *coefs,
 													  const int *clip_coef, const double *dxi, const double *dyi, double *dxl, double *dyl,
-													  double *scratch, int lp_filt, int smem_doubles, double *shot_minmax) {
+													  double *scratch, int lp_filt, int smem_doubles, double *shot_minmax,
+													  int loess_filt, double loess_w_secs, int degree) {
 	extern __shared__ double lp_smem[];
 	const int id = blockIdx.x, lane = threadIdx.x;
 	if (id >= n_shots * 2) return;
@@ -414,6 +428,40 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 		vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
 	}
 	if (lane == 0 && shot_minmax != nullptr) { shot_minmax[(size_t)id * 2] = vmin; shot_minmax[(size_t)id * 2 + 1] = vmax; }
+	// The LOESS / Savitzky-Golay estimate of a frame whose window is not clamped by the shot's ends is a fixed linear
+	// combination of the window: the weights depend on the offset only, so b0 = sum_k coef[k] * (y[j - h + k] - y[j]).
+	// The coefficients of the shot go to the start of its scratch area (the spline data there is dead by now).
+	if (axis == 0 && cl >= 10) {
+		__syncwarp();
+		const double fr = clips[sh.clip].fr;
+		int win = min((int)(fr * loess_w_secs), cl - 2);
+		if ((win & 1) == 0) win -= 1;
+		const int h = (win - 1) >> 1;
+		double *coef = scratch + sh.scratch_base;
+		if (h >= 1) {
+			double s0 = 0, s2 = 0, s4 = 0;
+			for (int k = lane; k < win; k += 32) {
+				const double u = (double)(k - h) / (double)h;
+				double w = 1.0;
+				if (loess_filt) { const double r = fabs(u); const double c = 1.0 - r * r * r; w = c * c * c; }
+				const double wu2 = w * u * u;
+				s0 += w; s2 += wu2; s4 += wu2 * u * u;
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+				s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+				s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+			}
+			for (int k = lane; k < win; k += 32) {
+				const double u = (double)(k - h) / (double)h;
+				double w = 1.0;
+				if (loess_filt) { const double r = fabs(u); const double c = 1.0 - r * r * r; w = c * c * c; }
+				// symmetric window: s1 = s3 = 0, so Cramer's rule leaves (s2 s4 - s2^2 u^2) / (s0 s2 s4 - s2^3); degree 1: 1 / s0
+				coef[k] = (degree >= 2) ? w * (s2 * s4 - s2 * s2 * u * u) / (s0 * s2 * s4 - s2 * s2 * s2) : w / s0;
+			}
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -432,7 +480,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n_frames_total, const ClipDev *clips,
 							  const double *dxl, const double *dyl, double *dxs, double *dys, int loess_filt,
-							  double loess_w_secs, int degree, const double *shot_minmax) {
+							  double loess_w_secs, int degree, const double *shot_minmax, const double *scratch) {
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (gw >= n_frames_total * 2) return;
@@ -459,6 +507,16 @@ __global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n
 	const double ymin = shot_minmax[((size_t)shot * 2 + axis) * 2], ymax = shot_minmax[((size_t)shot * 2 + axis) * 2 + 1];
 	if (loess_filt && !(ymax > ymin)) {
 		if (lane == 0) out[j] = y[j];
+		return;
+	}
+	if (h >= 1 && j - h >= 0 && j + h <= cl - 1) {
+		// window not clamped: fixed coefficients (lowpass_kernel)
+		const double *coef = scratch + sh.scratch_base;
+		const double yj = y[j];
+		double acc = 0.0;
+		for (int i = lane; i < win; i += 32) acc += coef[i] * (y[lo + i] - yj);
+		acc = warp_sum(acc);
+		if (lane == 0) out[j] = acc + yj;
 		return;
 	}
 	const double dmax = (double)max(j - lo, lo + win - 1 - j);
@@ -702,6 +760,45 @@ __global__ void __launch_bounds__(256) transpose_hwn_kernel(const uint8_t *__res
 			const int valid = W - 4 * c;     // bytes of this word that are pixels
 			if (valid < 4) v &= (1u << (8 * valid)) - 1u;
 			*reinterpret_cast<uint32_t *>(out + (size_t)r * map_stride + 4 * c) = v;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// The renderer's per-frame crop: sc_renderer, smartVidCrop.py:1906-1912,
+//   out[f] = frame[f][by1:by2, bx1:bx2, :]
+// for interleaved uint8 frames [F][H][W][C].  Pure data movement: every thread produces VEC aligned bytes of the packed
+// output; the source row segment starts at an arbitrary byte (bx1 * C), so a thread loads the aligned 32-bit words that
+// cover its bytes (neighbouring threads share them through L1) and funnel-shifts them into place.  VEC = 8 or 4 when the
+// output row length is a multiple of it, else 1 (byte per thread).
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) crop_frames_kernel(const uint8_t *__restrict__ frames, int n_frames, int H, int W, int C,
+														   const int32_t *__restrict__ boxes, int oh, int ow, uint8_t *__restrict__ out) {
+	const long long row_bytes = (long long)ow * C;
+	const long long vec_per_row = row_bytes / VEC;
+	const long long total = (long long)n_frames * oh * vec_per_row;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const long long r = i / vec_per_row;              // output row (frame * oh + y)
+		const int v = (int)(i - r * vec_per_row);
+		const int f = (int)(r / oh), y = (int)(r - (long long)f * oh);
+		const int bx1 = boxes[f * 4 + 0], by1 = boxes[f * 4 + 1];
+		const uint8_t *src = frames + (((long long)f * H + (by1 + y)) * W + bx1) * C + (long long)v * VEC;
+		uint8_t *dst = out + r * row_bytes + (long long)v * VEC;
+		if constexpr (VEC == 1) {
+			*dst = *src;
+		} else {
+			const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+			const uint32_t *w0 = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+			const unsigned sh = (unsigned)(a & 3) * 8u;
+			uint32_t w[VEC / 4 + 1];
+#pragma unroll
+			for (int k = 0; k <= VEC / 4; ++k) w[k] = (k < VEC / 4 || sh != 0u) ? __ldg(w0 + k) : 0u;   // (no read past the segment when aligned)
+			uint32_t o[VEC / 4];
+#pragma unroll
+			for (int k = 0; k < VEC / 4; ++k) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+			if constexpr (VEC == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
+			else *reinterpret_cast<uint32_t *>(dst) = o[0];
 		}
 	}
 }

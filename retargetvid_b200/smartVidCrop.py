@@ -106,8 +106,8 @@ def smart_crop_version():
 
 def _check_supported(CP):
 	if float(CP['resize_factor']) != 1.0:
-		if not float(CP['resize_factor']) > 1.0 or float(CP['resize_factor']) == 2.0:
-			raise NotImplementedError('resize_factor=%r: exact 2x (OpenCV switches to INTER_AREA) and up-scaling are not built' % CP['resize_factor'])
+		if not float(CP['resize_factor']) > 1.0:
+			raise NotImplementedError('resize_factor=%r: up-scaling before the clustering is not built' % CP['resize_factor'])
 		if CP['resize_type'] not in (1, 3):
 			raise NotImplementedError('resize_type=2 (cubic) is not built')
 
@@ -312,6 +312,13 @@ def smart_vid_crop(video_path, CP=None,
 	# (the reference ends with gc.collect() to drop its frame buffers, smartVidCrop.py:2612; nothing of that size lives here
 	# and a full collection costs more than the whole GPU pass of a clip)
 	return VD, smart_crop_results
+
+
+def crop_frames(frames, bbs, device=0):
+	"""The per-frame crop of the reference's renderer (sc_renderer, smartVidCrop.py:1906-1912) on the GPU:
+	frames uint8 [F, h_orig, w_orig, C], bbs = VD['bbs'] -> uint8 [F, fbb_h, fbb_w, C] with
+	out[f] == frames[f][y1:y2, x1:x2, :].  Decoding and encoding the video stay with the caller (out of scope)."""
+	return _engine(device).ctx.crop_frames(frames, bbs)
 
 
 def write_result_files(results_out, suffix, vid_data, info_dict):

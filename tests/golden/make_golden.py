@@ -148,6 +148,9 @@ CLIPS = {
 	'border_hd_multishot': (dict(seed=2018, fc=260, w_orig=1920, h_orig=1080, shot_starts=[70, 150]), dict(t_border=12), ['3:1', '9:16']),
 	'loess_w3_bias': (dict(seed=2019, fc=320, shot_starts=[200]),
 					dict(loess_w_secs=3, value_bias=0.5, t_threshold=140, lp_cutoff=1.5, hdbscan_min=15), ['4:5']),
+	# exactly 2x: cv2.resize turns INTER_LINEAR into INTER_AREA (resize.cpp, is_area_fast); 4:3 input -> 187 x 250 maps, odd height
+	'resize_area2': (dict(seed=2020, fc=110, w_orig=480, h_orig=360, shot_starts=[60]),
+					dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=2, resize_type=1, select_sum=1), ['9:16']),
 	# a different sampling table: every 3rd frame gets a map, 24 fps
 	'skip3_fr24': (dict(seed=2016, fc=150, fr=24.0, skip=3, shot_starts=[75]), {}, ['9:16']),
 }

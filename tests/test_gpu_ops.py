@@ -190,7 +190,44 @@ def test_iou_per_annotator_length_and_malformed_boxes(engine):
 		for u in range(2):
 			want = eval_oracle.video_iou([list(b) for b in method[v]], [list(b) for b in annots[u][v]], fc[v])
 			assert vid_iou[i][u] == want, (v, u)
+	# a box with x2 < x1 has a negative area; its intersection with anything is 0, so the IoU is 0 / (aA + aB): 0.0 like the
+	# reference unless the union is exactly 0, where the reference raises ZeroDivisionError -> loud error here too
 	bad = {5: method[5].copy(), 9: method[9]}
-	bad[5][3] = [400, 10, 100, 50]           # x2 < x1
+	bad[5][3] = [5, 0, 0, 0]                 # area (0 - 5 + 1) * 1 = -4
+	ann_bad = [{5: annots[0][5].copy(), 9: annots[0][9]}, annots[1]]
+	ann_bad[0][5][3] = [0, 0, 1, 1]          # area 4: union 0
 	with pytest.raises(_cabi.RvbError):
-		rev.evaluate_arrays(engine.ctx, bad, annots, fc)
+		rev.evaluate_arrays(engine.ctx, bad, ann_bad, fc)
+	ok = {5: method[5].copy(), 9: method[9]}
+	ok[5][3] = [400, 10, 100, 50]            # x2 < x1 with a non-zero union: IoU 0.0, as the reference computes it
+	vid_iou2, _, _ = rev.evaluate_arrays(engine.ctx, ok, annots, fc)
+	assert vid_iou2[0][0] == eval_oracle.video_iou([list(b) for b in ok[5]], [list(b) for b in annots[0][5]], fc[5])
+
+
+def test_renderer_crop_equals_numpy_slicing(engine):
+	"""rvb_crop_frames / smartVidCrop.crop_frames: out[f] == frame[f][y1:y2, x1:x2, :] (sc_renderer,
+	smartVidCrop.py:1906-1912) for row lengths that are multiples of 8 and of 4 bytes and for odd ones (202 x 3 bytes),
+	boxes from the crop track itself."""
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vd = synth.make_clip(8300, fc=40)
+	CP = svc.sc_init_crop_params()
+	res = svc.smart_vid_crop_batch([vd], CP, ['1:3', '9:16', '4:5', '3:1'])[0]
+	rng = np.random.default_rng(3)
+	frames = rng.integers(0, 256, (vd['fc'], vd['h_orig'], vd['w_orig'], 3)).astype(np.uint8)
+	for r in range(4):
+		bbs = res.boxes[r]
+		got = svc.crop_frames(frames, bbs)
+		for f in (0, 7, vd['fc'] - 1):
+			x1, y1, x2, y2 = (int(v) for v in bbs[f])
+			assert np.array_equal(got[f], frames[f][y1:y2, x1:x2, :]), (r, f)
+	# single channel, and a box that does not have the common size is refused
+	gray = np.ascontiguousarray(frames[:, :, :, 0:1])
+	got = svc.crop_frames(gray, res.boxes[0])
+	x1, y1, x2, y2 = (int(v) for v in res.boxes[0][5])
+	assert np.array_equal(got[5], gray[5][y1:y2, x1:x2, :])
+	bad = np.array(res.boxes[0])
+	bad[3, 2] += 1
+	with pytest.raises(_cabi.RvbError):
+		svc.crop_frames(frames, bad)

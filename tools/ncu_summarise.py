@@ -5,7 +5,10 @@
 """
 import csv
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
@@ -46,7 +49,8 @@ def main():
 		rd += k['dram_read_MB'] * 1e6
 		wr += k['dram_write_MB'] * 1e6
 		ks.append(k)
-	out = dict(source=source, maps=maps, dram_bytes_per_step=rd + wr, dram_bytes_read=rd, dram_bytes_written=wr,
+	import bench
+	out = dict(source=source, kernel_source_hash=bench._kernel_source_hash(), maps=maps, dram_bytes_per_step=rd + wr, dram_bytes_read=rd, dram_bytes_written=wr,
 			dram_bytes_per_map=(rd + wr) / maps, serialised_ms=sum(k['ms'] for k in ks), kernels=ks)
 	json.dump(out, open(dst, 'w'), indent=1)
 	print('%d launches, %.1f ms serialised, %.1f MB read, %.1f MB written, %.0f B/map' % (len(ks), out['serialised_ms'], rd / 1e6, wr / 1e6, out['dram_bytes_per_map']))
