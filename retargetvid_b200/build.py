@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'rvb.cu')
 OUT = os.path.join(HERE, 'lib', 'libretargetvid_b200.so')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('rvb.cu', 'map_kernel.cuh', 'prim_kernel.cuh', 'prim_retire.inc', 'track_kernels.cuh', 'iou_kernel.cuh')]
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('rvb.cu', 'map_kernel.cuh', 'prim_kernel.cuh', 'fprim_kernel.cuh', 'prim_retire.inc', 'track_kernels.cuh', 'iou_kernel.cuh')]
 DEPS.append(os.path.join(os.path.dirname(HERE), 'include', 'retargetvid_b200.h'))
 
 

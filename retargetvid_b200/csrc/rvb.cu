@@ -1314,11 +1314,30 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	}
 	Staging sg;
 	first[V] = (int)NF;
-	const long long chunks = (max_frames + 255) / 256;
-	if (chunks > 65535) return fail(RVB_ERR_INVALID, "a video of %lld frames (max 16.7 M per video)", max_frames);
+	// work items: every video padded to whole 32-frame warp slots; a chunk = 8 slots; per chunk the video of its first slot,
+	// that video's first slot, first frame and frame count
+	std::vector<int4> chunk_tab;
+	{
+		std::vector<long long> pad_first((size_t)V + 1);
+		long long slots = 0;
+		for (int v = 0; v < V; ++v) {
+			pad_first[v] = slots;
+			slots += (b->frame_offset[v + 1] - b->frame_offset[v] + 31) / 32;
+		}
+		if (slots < 1) return fail(RVB_ERR_INVALID, "no frames");
+		pad_first[V] = slots;
+		chunk_tab.resize((size_t)((slots + 7) / 8));
+		int v = 0;
+		for (size_t ci = 0; ci < chunk_tab.size(); ++ci) {
+			while (v + 1 < V && (long long)ci * 8 >= pad_first[v + 1]) ++v;
+			chunk_tab[ci] = make_int4(v, (int)pad_first[v], (int)b->frame_offset[v], (int)(b->frame_offset[v + 1] - b->frame_offset[v]));
+		}
+	}
+	const size_t o_chunks = sg.add(chunk_tab.data(), chunk_tab.size() * sizeof(int4));
 	const size_t o_first = sg.add(first.data(), (size_t)(V + 1) * sizeof(int));
 	const size_t o_ne = sg.add(neval.data(), (size_t)V * U * sizeof(int));
 	const size_t o_acc = sg.add(nullptr, (size_t)V * U * 2 * sizeof(uint64_t));
+	const size_t o_acc3 = sg.add(nullptr, (size_t)V * U * 4 * sizeof(uint64_t));
 	const size_t o_bad = sg.add(nullptr, sizeof(int));
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
 	if (c->stage.ensure(sg.bytes.size()) || c->iou_a.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
@@ -1342,15 +1361,38 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 		}
 	}
 	unsigned long long *d_acc = (unsigned long long *)(M + o_acc);
-	CU(cudaMemsetAsync(d_acc, 0, (size_t)V * U * 2 * sizeof(uint64_t), st));
+	unsigned long long *d_acc3 = (unsigned long long *)(M + o_acc3);
+	CU(cudaMemsetAsync(d_acc3, 0, (size_t)V * U * 4 * sizeof(uint64_t), st));
 	int *d_bad = (int *)(M + o_bad);
 	CU(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
 	CU(cudaEventRecord(c->ev_iou0, st));
-	iou_kernel<<<dim3((unsigned)V, (unsigned)chunks), 256, 0, st>>>(d_method, d_annot, (const int *)(M + o_first),
-															(const int *)(M + o_ne), NF, U, d_fiou, d_acc, d_bad);
+	const int n_chunks = (int)chunk_tab.size();
+	{
+		const int *d_first = (const int *)(M + o_first), *d_ne = (const int *)(M + o_ne);
+		const int4 *d_chunks = (const int4 *)(M + o_chunks);
+		static const bool generic = getenv("RVB_IOU_GENERIC") != nullptr;
+		// persistent grid: exactly the CTAs that are resident at once
+#define RVB_IOU_LAUNCH(UT) { static int occ = 0; if (!occ) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_kernel<UT, false>, 256, 0)); occ = std::max(occ, 1); } \
+		if (d_fiou) iou_kernel<UT, true><<<std::min(n_chunks, c->n_sm * occ), 256, 0, st>>>(d_method, d_annot, d_first, V, d_ne, d_chunks, n_chunks, NF, U, d_fiou, d_acc3, d_bad); \
+		else iou_kernel<UT, false><<<std::min(n_chunks, c->n_sm * occ), 256, 0, st>>>(d_method, d_annot, d_first, V, d_ne, d_chunks, n_chunks, NF, U, d_fiou, d_acc3, d_bad); }
+		switch (generic ? 0 : U) {
+			case 1: RVB_IOU_LAUNCH(1) break;
+			case 2: RVB_IOU_LAUNCH(2) break;
+			case 3: RVB_IOU_LAUNCH(3) break;
+			case 4: RVB_IOU_LAUNCH(4) break;
+			case 5: RVB_IOU_LAUNCH(5) break;
+			case 6: RVB_IOU_LAUNCH(6) break;      // the RetargetVid annotations: 6 annotators
+			case 7: RVB_IOU_LAUNCH(7) break;
+			case 8: RVB_IOU_LAUNCH(8) break;
+			default: RVB_IOU_LAUNCH(0) break;
+		}
+#undef RVB_IOU_LAUNCH
+	}
+	iou_finish_kernel<<<(V * U + 255) / 256, 256, 0, st>>>(d_acc3, V * U, d_acc);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev_iou1, st));
 	c->iou_timed = true;
+	c->launches += 1;
 	c->launches += 1;
 	const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
 	CU(cudaMemcpyAsync(b->acc, d_acc, (size_t)V * U * 2 * sizeof(uint64_t), kind, st));

@@ -19,10 +19,13 @@ from . import _cabi
 _CTX = {}
 
 
-def _ctx(device_index):
-	if device_index not in _CTX:
-		_CTX[device_index] = _cabi.Context(device_index)
-	return _CTX[device_index]
+def _ctx(device_index, stream_ptr):
+	"""One library context (workspace) per (device, CUDA stream): calls on different streams may be in flight together."""
+	key = (device_index, int(stream_ptr))
+	if key not in _CTX:
+		_CTX[key] = _cabi.Context(device_index)
+		_CTX[key].set_stream(stream_ptr)
+	return _CTX[key]
 
 
 _IPARAMS = ['t_threshold', 'clust_filt', 'hdbscan_min', 'hdbscan_min_samples', 'select_sum', 'op_close', 'com_km', 't_border',
@@ -58,13 +61,15 @@ torch.library.define(
 
 @torch.library.impl('retargetvid_b200::crop_track', 'CUDA')
 def _crop_track_cuda(maps, clips, fr, shots, true_inds, ratio_w, ratio_h, iparams, fparams):
-	"""maps: device tensor, float32 [N,H,W] (log-saliency) or uint8 [N,H,W'] with W' >= W a multiple of 4 (the columns
-	x >= w_process are ignored); the process width is W for float32 and comes from... (uint8: W' if it is not padded).
-	Returns (boxes int32 [R, sum F, 4] = x1,y1,x2,y2, centres float64 [2, sum N], status int32 [n_clips] on the host)."""
+	"""maps: device tensor, float32 [N,H,W] (log-saliency, W = process width) or uint8 [N,H,W'] where W' is the row
+	stride, a multiple of 4: 256 means the device-native layout of a 250-pixel-wide map (6 ignored padding bytes per row),
+	anything else is taken as the process width itself.
+	Returns (boxes int32 [R, sum F, 4] = x1,y1,x2,y2, centres float64 [2, sum N], status int32 [n_clips]), all on the device."""
 	if not maps.is_cuda or maps.dim() != 3 or not maps.is_contiguous():
 		raise ValueError('maps must be a contiguous CUDA tensor [N, H, W]')
 	dev = maps.device.index if maps.device.index is not None else torch.cuda.current_device()
-	ctx = _ctx(dev)
+	stream_ptr = torch.cuda.current_stream(maps.device).cuda_stream
+	ctx = _ctx(dev, stream_ptr)
 	nc = int(clips.shape[0])
 	R = len(ratio_w)
 	carr = (_cabi.rvb_clip * nc)()
@@ -114,7 +119,6 @@ def _crop_track_cuda(maps, clips, fr, shots, true_inds, ratio_w, ratio_h, iparam
 	b.boxes = boxes.data_ptr()
 	b.centres = centres.data_ptr()
 	b.clip_status = status.data_ptr()
-	ctx.set_stream(torch.cuda.current_stream(maps.device).cuda_stream)
 	ctx.crop_track_batch(p, b)
 	return boxes, centres, status
 

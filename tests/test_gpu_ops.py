@@ -231,3 +231,62 @@ def test_renderer_crop_equals_numpy_slicing(engine):
 	bad[3, 2] += 1
 	with pytest.raises(_cabi.RvbError):
 		svc.crop_frames(frames, bad)
+
+
+def test_iou_division_and_exact_mean_on_random_boxes_at_size(engine):
+	"""300k frames x 3 annotators of random well-formed boxes (extents 1 .. 8191 and a few beyond, so both integer paths
+	run; disjoint pairs; videos of 1, 31, 32, 33, 255 ... frames so that every padding case of the warp slots occurs):
+	every per-frame IoU equals numpy's IEEE division of the two integers bit for bit (retargetvid_eval.py:10-27), every
+	per-(video, annotator) mean equals the exactly rounded mean of those doubles (statistics.mean, :193)."""
+	import statistics
+	from fractions import Fraction
+	from retargetvid_b200 import _cabi
+	rng = np.random.default_rng(2024)
+	lens = [1, 31, 32, 33, 255, 256, 257, 613, 7, 1000] * 80
+	lens += [int(v) for v in rng.integers(1, 2000, 120)]
+	V, U = len(lens), 3
+	foff = np.zeros(V + 1, dtype=np.int64)
+	foff[1:] = np.cumsum(lens)
+	NF = int(foff[-1])
+
+	def boxes(n, big_every):
+		w = rng.integers(1, 8192, n)
+		h = rng.integers(1, 8192, n)
+		big = (np.arange(n) % big_every) == 0
+		w[big] += 9000
+		h[big] = h[big] % 4000 + 1             # unions stay below 2^28 (the fixed point holds IoUs >= 2^-28 exactly)
+		x1 = rng.integers(0, 12000, n)
+		y1 = rng.integers(0, 12000, n)
+		# a third of the boxes small and close together so that intersections are common
+		near = rng.random(n) < 0.6
+		x1[near] %= 300
+		y1[near] %= 300
+		return np.stack([x1, y1, x1 + w - 1, y1 + h - 1], axis=1).astype(np.int32)
+	method = boxes(NF, 997)
+	annot = np.stack([boxes(NF, 1013 + u) for u in range(U)])
+	neval = np.tile(np.array(lens, dtype=np.int32)[:, None], (1, U))
+	neval[5, 1] = max(1, lens[5] // 2)          # one annotator stops early
+	fiou = np.empty((U, NF), dtype=np.float64)
+	acc = np.zeros((V, U, 2), dtype=np.uint64)
+	ib = _cabi.rvb_iou_batch()
+	ib.n_videos, ib.n_users, ib.mem_space = V, U, _cabi.RVB_MEM_HOST
+	ib.frame_offset = foff.ctypes.data
+	ib.n_eval_user = neval.ctypes.data
+	ib.method_boxes, ib.annot_boxes, ib.frame_iou, ib.acc = method.ctypes.data, annot.ctypes.data, fiou.ctypes.data, acc.ctypes.data
+	engine.ctx.iou_batch(ib)
+	m = method.astype(np.int64)
+	for u in range(U):
+		g = annot[u].astype(np.int64)
+		iw = np.maximum(0, np.minimum(g[:, 2], m[:, 2]) - np.maximum(g[:, 0], m[:, 0]) + 1)
+		ih = np.maximum(0, np.minimum(g[:, 3], m[:, 3]) - np.maximum(g[:, 1], m[:, 1]) + 1)
+		inter = iw * ih
+		uni = (g[:, 2] - g[:, 0] + 1) * (g[:, 3] - g[:, 1] + 1) + (m[:, 2] - m[:, 0] + 1) * (m[:, 3] - m[:, 1] + 1) - inter
+		want = inter.astype(np.float64) / uni.astype(np.float64)
+		assert (inter > 0).sum() > NF // 10
+		assert np.array_equal(fiou[u].view(np.uint64), want.view(np.uint64)), int((fiou[u] != want).sum())
+		for v in list(range(0, V, 37)) + [5]:
+			n = int(neval[v, u])
+			vals = want[foff[v]:foff[v] + n]
+			exact = sum((Fraction(float(x)) for x in vals), Fraction(0)) / n
+			got = engine.ctx.iou_mean_from_acc(acc[v, u, 0], acc[v, u, 1], n)
+			assert got == float(exact) == statistics.mean([float(x) for x in vals]), (v, u)
