@@ -258,12 +258,12 @@ class Workload(object):
 
 
 def _kernel_source_hash():
+	"""Hash of the device code of the map pipeline (the kernels profiles/map_kernel_traffic.json was captured on)."""
 	import hashlib
 	h = hashlib.sha256()
 	d = os.path.join(ROOT, 'retargetvid_b200', 'csrc')
-	for f in sorted(os.listdir(d)):
-		if f.endswith(('.cu', '.cuh', '.inc')):
-			h.update(open(os.path.join(d, f), 'rb').read())
+	for f in ('map_kernel.cuh', 'prim_kernel.cuh', 'prim_retire.inc', 'fprim_kernel.cuh'):
+		h.update(open(os.path.join(d, f), 'rb').read())
 	return h.hexdigest()[:16]
 
 
@@ -701,7 +701,7 @@ def gpu_arm(args, rank, world, local_rank):
 			'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
 						'traffic': traffic, 'traffic_source': traffic_note,
 						'kernel': 'map pipeline of a step: rvb::map_kernel<256,16,Front> -> per size class rvb::prim_kernel<NW,KMAX> -> rvb::map_kernel<NT,TPT,Back> '
-								'(5 classes side by side on their own streams), cut-adjacent chains in rvb::map_kernel<NT,TPT,Mono> x5 on a side stream '
+								'(the size classes one after the other on the main stream), cut-adjacent chains in rvb::map_kernel<NT,TPT,Mono> x5 on a side stream '
 								'(joined before the end event)',
 						'algorithmic_bytes_per_step': algo, 'kernel_ms_per_step': map_ms / args.steps,
 						'kernel_launches_per_step': map_launches / args.steps,

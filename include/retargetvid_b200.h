@@ -42,6 +42,10 @@ extern "C" {
 #define RVB_MAPS_U8_HWN        1  /* uint8 per clip [H][W][N], the reference's vid_data['smaps'] (smartVidCrop.py:286) */
 #define RVB_MAPS_F32_NHW       2  /* float32 log-saliency [sum N][H][W], UNISAL output before unisal/train.py:1270-1274 */
 
+/* layout of the optional filtered-map output */
+#define RVB_FILTERED_NHW       0  /* uint8 [sum N][H][row_stride_out] */
+#define RVB_FILTERED_HWN       1  /* uint8 per clip [H][W][n_maps], packed back to back (the reference's layout) */
+
 typedef struct rvb_ctx rvb_ctx;
 
 /* Mirrors the crop_params dict of sc_init_crop_params (smartVidCrop.py:132-209);
@@ -114,9 +118,11 @@ typedef struct rvb_batch {
 	double  *map_scores;          /* optional [sum N]: mean_sal_scores (smartVidCrop.py:1307) */
 	double  *clip_scores;         /* optional [n_clips][1 + n_ratios]: mean_sal_score, mean_cvrg_score per ratio */
 	int32_t *clip_dims;           /* optional [n_clips][n_ratios][9]: conversion_mode, w_final, h_final, fbb_w, fbb_h, border t,b,l,r */
-	uint8_t *filtered_maps;       /* optional uint8 [sum N][H][row_stride_out] after clustering/closing/blend */
-	int32_t row_stride_out;
-	int32_t reserved1;
+	uint8_t *filtered_maps;       /* optional, the maps after clustering/closing/blend: uint8 [sum N][H][row_stride_out]
+	                                 (RVB_FILTERED_NHW), or per clip [H][W][n_maps] packed like RVB_MAPS_U8_HWN input
+	                                 (RVB_FILTERED_HWN: what smart_vid_crop leaves in vid_data['smaps'], smartVidCrop.py:2366-2373) */
+	int32_t row_stride_out;       /* RVB_FILTERED_NHW only; 0 = the library's 256-byte-aligned rows */
+	int32_t filtered_layout;      /* RVB_FILTERED_* */
 	int32_t *map_info;            /* optional [sum N][4]: n_points, n_clusters, kept_points, flags */
 	int32_t *clip_status;         /* optional [n_clips]: RVB_OK or RVB_ERR_* per clip */
 	const void *const *clip_maps; /* optional HOST array of n_clips pointers (each in mem_space): per-clip map blocks

@@ -23,6 +23,7 @@ RVB_MAX_POINTS = 8192
 RVB_MAX_RATIOS = 8
 RVB_MEM_HOST = 0
 RVB_MEM_DEVICE = 1
+RVB_FILTERED_NHW, RVB_FILTERED_HWN = 0, 1
 RVB_MAPS_U8_NHW = 0
 RVB_MAPS_U8_HWN = 1
 RVB_MAPS_F32_NHW = 2
@@ -67,7 +68,7 @@ class rvb_batch(C.Structure):
 				('empty', C.c_void_p),
 				('series', C.c_void_p), ('map_scores', C.c_void_p), ('clip_scores', C.c_void_p),
 				('clip_dims', C.c_void_p), ('filtered_maps', C.c_void_p), ('row_stride_out', C.c_int32),
-				('reserved1', C.c_int32), ('map_info', C.c_void_p), ('clip_status', C.c_void_p),
+				('filtered_layout', C.c_int32), ('map_info', C.c_void_p), ('clip_status', C.c_void_p),
 				('clip_maps', C.POINTER(C.c_void_p))]
 
 

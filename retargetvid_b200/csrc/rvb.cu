@@ -111,7 +111,7 @@ struct rvb_ctx {
 	                            // RVB_CHAIN_MONO=1: the monolithic kernel walks them instead (the round-1 default)
 	int prim_variant[4] = {0, 0, 0, 0};
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
-	DevBuf maps_in, maps_nhw, filt, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
+	DevBuf maps_in, maps_nhw, filt, filt_hwn, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
 	DevBuf scr_pinfo, scr_val, scr_pkey, scr_far, scr_alist;
 	bool dense_prim = true;    // the all-pairs prim_kernel (default, the faster one as measured: DESIGN.md 4.1);
 	                           // RVB_FRONTIER_PRIM=1: the lattice-local fprim_kernel (exact too, kept for the record)
@@ -452,7 +452,7 @@ extern "C" int rvb_ctx_destroy(rvb_ctx *c) {
 	if (!c) return RVB_OK;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = {&c->maps_in, &c->maps_nhw, &c->filt, &c->meta, &c->mapout, &c->series, &c->scratch,
+	DevBuf *bufs[] = {&c->maps_in, &c->maps_nhw, &c->filt, &c->filt_hwn, &c->meta, &c->mapout, &c->series, &c->scratch,
 					  &c->boxes, &c->misc, &c->iou_a, &c->iou_b, &c->iou_c, &c->scr_pinfo, &c->scr_val, &c->scr_pkey,
 					  &c->scr_far, &c->scr_alist};
 	for (DevBuf *b : bufs) b->release();
@@ -1238,8 +1238,28 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	if (want_filtered) {
 		const int so = b->row_stride_out > 0 ? b->row_stride_out : WPS;
 		if (so < W) return fail(RVB_ERR_INVALID, "row_stride_out=%d", so);
-		// slot m holds map m: all rows of all maps in one strided copy
-		outs.push_back({b->filtered_maps, c->filt.p, 0, (size_t)WPS, (size_t)W, (size_t)NM * H, (size_t)so});
+		if (b->filtered_layout == RVB_FILTERED_HWN) {
+			// the reference's own layout, per clip [H][W][n_maps] packed back to back: transposed on the device
+			uint8_t *d_hwn = b->filtered_maps;
+			if (host) {
+				if (c->filt_hwn.ensure((size_t)NM * H * W)) return RVB_ERR_CUDA;
+				d_hwn = (uint8_t *)c->filt_hwn.p;
+			}
+			int max_maps = 1;
+			for (int i = 0; i < nc; ++i) max_maps = std::max(max_maps, clips[i].n_maps);
+			for (int z0 = 0; z0 < nc; z0 += 65535) {
+				dim3 grid((max_maps + kTrMaps - 1) / kTrMaps, H, std::min(nc - z0, 65535));
+				transpose_to_hwn_kernel<<<grid, 256, 0, st>>>((const uint8_t *)c->filt.p, WPS, d_clips + z0, H, W, d_hwn);
+				c->launches += 1;
+			}
+			CU(cudaGetLastError());
+			if (host) outs.push_back({b->filtered_maps, d_hwn, (size_t)NM * H * W, 0, 0, 0, 0});
+		} else if (b->filtered_layout != RVB_FILTERED_NHW) {
+			return fail(RVB_ERR_INVALID, "filtered_layout=%d", b->filtered_layout);
+		} else {
+			// slot m holds map m: all rows of all maps in one strided copy
+			outs.push_back({b->filtered_maps, c->filt.p, 0, (size_t)WPS, (size_t)W, (size_t)NM * H, (size_t)so});
+		}
 	}
 	if (host) {
 		for (const Out &o : outs) {

@@ -764,6 +764,56 @@ __global__ void __launch_bounds__(256) transpose_hwn_kernel(const uint8_t *__res
 	}
 }
 
+// The way back for the filtered maps a caller wants in the reference layout (vid_data['smaps'] after smart_vid_crop,
+// smartVidCrop.py:2366-2373): [N][H][WPS] -> per clip [H][W][n_maps], packed back to back like the input.
+//   in : per map the row's W bytes as aligned 32-bit words into the tile (row stride 65 words);
+//   out: per pixel a run of <= 60 bytes at an arbitrary alignment -> half a warp writes the <= 16 aligned words that cover
+//        it: whole words as 32-bit stores, the two partial words at the ends byte by byte (their other bytes belong to the
+//        neighbouring runs, written by other CTAs).
+__global__ void __launch_bounds__(256) transpose_to_hwn_kernel(const uint8_t *__restrict__ src, int WPS, const ClipDev *__restrict__ clips,
+																int H, int W, uint8_t *__restrict__ dst_all) {
+	__shared__ uint32_t tile32[kTrMaps * kTrStrideW];
+	const uint8_t *tile = reinterpret_cast<const uint8_t *>(tile32);
+	const ClipDev cd = clips[blockIdx.z];
+	const int N = cd.n_maps;
+	const int n0 = blockIdx.x * kTrMaps;
+	if (n0 >= N) return;
+	const int nb = min(kTrMaps, N - n0);
+	const int y = blockIdx.y;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int half = lane >> 4, hl = lane & 15;
+	const int words = (W + 3) >> 2;
+	const uint8_t *in = src + ((size_t)(cd.map_offset + n0) * H + y) * WPS;
+	const size_t map_stride = (size_t)H * WPS;
+	for (int i = tid; i < nb * 64; i += 256) {
+		const int r = i >> 6, c = i & 63;
+		if (c < words) tile32[r * kTrStrideW + c] = __ldg(reinterpret_cast<const uint32_t *>(in + (size_t)r * map_stride) + c);
+	}
+	__syncthreads();
+	const uintptr_t clip0 = reinterpret_cast<uintptr_t>(dst_all) + (size_t)cd.map_offset * H * W;
+	for (int x = warp * 2 + half; x < W; x += 16) {
+		const uintptr_t seg = clip0 + ((size_t)y * W + x) * N + n0;
+		const uintptr_t a = (seg & ~(uintptr_t)3) + 4u * hl;
+		const int nl0 = (int)((long long)a - (long long)seg);       // map index (inside the tile) of byte 0 of this word
+		if (nl0 >= nb || nl0 + 3 < 0) continue;
+		uint32_t v = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int nl = nl0 + k;
+			if (nl >= 0 && nl < nb) v |= (uint32_t)tile[(size_t)nl * (kTrStrideW * 4) + x] << (8 * k);
+		}
+		if (nl0 >= 0 && nl0 + 3 < nb) {
+			*reinterpret_cast<uint32_t *>(a) = v;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const int nl = nl0 + k;
+				if (nl >= 0 && nl < nb) *reinterpret_cast<uint8_t *>(a + k) = (uint8_t)(v >> (8 * k));
+			}
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // The renderer's per-frame crop: sc_renderer, smartVidCrop.py:1906-1912,
 //   out[f] = frame[f][by1:by2, bx1:bx2, :]

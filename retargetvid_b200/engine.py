@@ -20,7 +20,7 @@ def parse_ratio(out_ratio):
 class ClipResult(object):
 	"""Per-clip outputs of one batched call (numpy views / python scalars)."""
 	__slots__ = ('status', 'boxes', 'dx', 'dy', 'dxnf', 'dynf', 'jumps', 'empty', 'series', 'map_scores', 'mean_sal_score',
-				'cvrg_scores', 'dims', 'map_info', 'filtered')
+				'cvrg_scores', 'dims', 'map_info', 'filtered', 'filtered_hwn')
 
 
 class CropEngine(object):
@@ -126,7 +126,12 @@ class CropEngine(object):
 			b.empty = empty.ctypes.data
 			b.map_scores = mscores.ctypes.data
 			b.map_info = minfo.ctypes.data
-		if want_filtered:
+		if want_filtered == 'hwn':
+			# the reference's layout: per clip [H][W][n_maps], packed back to back
+			filt = np.empty(NM * H * W, dtype=np.uint8)
+			b.filtered_maps = filt.ctypes.data
+			b.filtered_layout = _cabi.RVB_FILTERED_HWN
+		elif want_filtered:
 			filt = np.empty((NM, H, W), dtype=np.uint8)
 			b.filtered_maps = filt.ctypes.data
 			b.row_stride_out = W
@@ -159,7 +164,10 @@ class CropEngine(object):
 				res.series = series[:, f0:f1]
 				res.map_scores = mscores[m0:m1]
 				res.map_info = minfo[m0:m1]
-			if want_filtered:
+			res.filtered_hwn = None
+			if want_filtered == 'hwn':
+				res.filtered_hwn = filt[m0 * H * W:m1 * H * W].reshape(H, W, m1 - m0)
+			elif want_filtered:
 				res.filtered = filt[m0:m1]
 			results[idxs[i]] = res
 		del keep

@@ -173,7 +173,9 @@ def _fill_vd(VD, CP, res, ratio_index, want_smaps):
 		ts += list(range(int(seg[1]) - int(seg[0]) + 1))
 	VD['ts'] = ts
 	VD['bbs'] = np.asarray(res.boxes[ratio_index]).tolist()      # python ints, [x1, y1, x2, y2] per frame
-	if want_smaps and res.filtered is not None:
+	if want_smaps and res.filtered_hwn is not None:
+		VD['smaps'] = res.filtered_hwn         # [H, W, N] as the reference leaves it (transposed on the GPU)
+	elif want_smaps and res.filtered is not None:
 		VD['smaps'] = np.ascontiguousarray(np.transpose(res.filtered, (1, 2, 0)))
 	return VD
 
@@ -286,7 +288,7 @@ def smart_vid_crop(video_path, CP=None,
 	VD['segm_backup'] = np.asarray(VD['segmentation']).copy()
 	t0 = time.perf_counter()
 	eng = _engine(device)
-	res = eng.run([VD], CP, [CP['out_ratio']], detail=True, want_filtered=True, cvrg_window=cvrg_window,
+	res = eng.run([VD], CP, [CP['out_ratio']], detail=True, want_filtered='hwn', cvrg_window=cvrg_window,
 				raise_on_clip_error=False)[0]
 	t_total = time.perf_counter() - t0
 	t_map = eng.ctx.last_map_kernel_ms()[0] / 1000.0

@@ -290,3 +290,21 @@ def test_iou_division_and_exact_mean_on_random_boxes_at_size(engine):
 			exact = sum((Fraction(float(x)) for x in vals), Fraction(0)) / n
 			got = engine.ctx.iou_mean_from_acc(acc[v, u, 0], acc[v, u, 1], n)
 			assert got == float(exact) == statistics.mean([float(x) for x in vals]), (v, u)
+
+
+def test_filtered_maps_in_the_reference_layout(engine):
+	"""RVB_FILTERED_HWN: the filtered maps come back per clip as [H][W][n_maps] (what smart_vid_crop leaves in
+	vid_data['smaps'], smartVidCrop.py:2366-2373), transposed on the device -- equal to the [N][H][W] output, for clips
+	with 1 .. >60 maps (several map tiles, every alignment of the per-pixel runs)."""
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	CP = svc.sc_init_crop_params()
+	vds = [synth.make_clip(8800 + i, fc=fc, shot_starts=ss) for i, (fc, ss) in enumerate(
+		[(6, []), (45, []), (300, [150]), (413, [100, 101, 300]), (1000, [500]), (59, []), (367, [])])]
+	a = engine.run(vds, CP, ['1:3'], detail=False, want_filtered=True)
+	b = engine.run(vds, CP, ['1:3'], detail=False, want_filtered='hwn')
+	assert max(int(vd['fc_sel']) for vd in vds) > 120
+	for ra, rb, vd in zip(a, b, vds):
+		assert rb.filtered_hwn.shape == (vd['h_process'], vd['w_process'], int(vd['fc_sel']))
+		assert np.array_equal(np.transpose(ra.filtered, (1, 2, 0)), rb.filtered_hwn)
+		assert np.array_equal(ra.boxes, rb.boxes)
