@@ -66,7 +66,7 @@ typedef struct rvb_params {
 	int32_t shift_time;           /* smartVidCrop.py:1740-1746 */
 	int32_t exit_on_low_cvrg;     /* compute the coverage score, smartVidCrop.py:2380-2383 */
 	int32_t cvrg_window;          /* 0: reference (score == 0.0), 1: crop-sized window */
-	int32_t resize_type;          /* 1 bilinear, 3 nearest (2 = cubic is not built), smartVidCrop.py:1079-1084 */
+	int32_t resize_type;          /* 1 bilinear, 2 cubic, 3 nearest: cv2.resize as called at smartVidCrop.py:1079-1084 */
 	int32_t focus_stability;      /* smartVidCrop.py:2427-2473 */
 	int32_t min_d_jump;
 	int32_t skip;                 /* frames between saliency maps, used by the focus-stability duration */

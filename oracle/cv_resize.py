@@ -4,7 +4,13 @@ modules/imgproc/src/resize.cpp: float32 source coordinate, weights rounded to 1/
 in int, vertical pass ((b*(S>>4))>>16, +2, >>2) with clipped rows) and INTER_NEAREST.  Checked against
 cv2 itself in tests/test_cpu_host.py.  For fx = fy = 1/2 OpenCV switches INTER_LINEAR to INTER_AREA
 (resize.cpp: is_area_fast && iscale == 2): resize_area2_u8 restates that path (full 2x2 cells (sum + 2) >> 2, the
-partial cells of an odd size saturate_cast<uchar>(float(sum) / count), i.e. round half to even)."""
+partial cells of an odd size saturate_cast<uchar>(float(sum) / count), i.e. round half to even).
+INTER_CUBIC (resize_type 2, smartVidCrop.py:1081-1082): resize_cubic_u8 -- interpolateCubic with A = -0.75 in float32,
+weights rounded to 1/2048 (short), horizontal pass in int over 4 taps with replicated borders, vertical pass as
+VResizeCubicVec_32s8u computes it: float32 S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) with b = beta / 2^22, rounded half to even,
+saturated.  That is what cv2 4.13 as installed here (IPP enabled) returns in every column at the factors tested in
+tests/test_cpu_host.py (2, 3, 4, 5, 1.5, 2.5); a build without IPP uses the integer formula (sum + 2^21) >> 22 in the last
+width % 8 columns, and IPP's own sampling deviates by +-1 on a few per cent of the pixels at factors such as 1.3 / 1.7."""
 import numpy as np
 
 
@@ -79,3 +85,43 @@ def resize_area2_u8(src):
 			else:
 				out[y, x] = cv_round(np.float32(blk.sum()) / np.float32(blk.size))
 	return out
+
+
+def _cubic_weights(x):
+	x = np.float32(x)
+	A, one = np.float32(-0.75), np.float32(1)
+	c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+	c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+	c2 = ((A + np.float32(2)) * (one - x) - (A + np.float32(3))) * (one - x) * (one - x) + one
+	c3 = one - c0 - c1 - c2
+	return [np.float32(c0), np.float32(c1), np.float32(c2), np.float32(c3)]
+
+
+def _cubic_coeffs(dsize, scale):
+	idx = np.zeros(dsize, dtype=np.int64)
+	a = np.zeros((dsize, 4), dtype=np.int64)
+	for d in range(dsize):
+		f = np.float32((d + 0.5) * scale - 0.5)
+		s = int(np.floor(f))
+		f = np.float32(f - np.float32(s))
+		idx[d] = s
+		a[d] = [cv_round(np.float32(c * np.float32(2048))) for c in _cubic_weights(f)]
+	return idx, a
+
+
+def resize_cubic_u8(src, fx, fy):
+	"""cv2.resize(src, None, fx=fx, fy=fy, interpolation=cv2.INTER_CUBIC) for uint8 (see the module docstring)."""
+	H, W = src.shape
+	dw, dh = cv_round(W * fx), cv_round(H * fy)
+	xi, xa = _cubic_coeffs(dw, 1.0 / fx)
+	yi, yb = _cubic_coeffs(dh, 1.0 / fy)
+	s = src.astype(np.int64)
+	rows = np.zeros((H, dw), dtype=np.int64)
+	for k in range(4):
+		rows += s[:, np.clip(xi - 1 + k, 0, W - 1)] * xa[:, k][None, :]
+	b = (yb.astype(np.float32) * (np.float32(1.0) / np.float32(2048 * 2048))).astype(np.float32)
+	R = [rows[np.clip(yi - 1 + k, 0, H - 1), :].astype(np.float32) for k in range(4)]
+	x = (R[3] * b[:, 3][:, None]).astype(np.float32)
+	for k in (2, 1, 0):
+		x = ((R[k] * b[:, k][:, None]).astype(np.float32) + x).astype(np.float32)
+	return np.clip(np.rint(x), 0, 255).astype(np.uint8)

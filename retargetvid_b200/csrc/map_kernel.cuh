@@ -111,11 +111,12 @@ struct MapArgs {
 	int32_t *labels_dbg;       // optional: labels of the single map being debugged
 	unsigned long long *phase_cycles;  // optional [16]: SM cycles spent per phase, summed over CTAs (profiling aid)
 	// resize_factor != 1 (smartVidCrop.py:1078-1084,1158,1184): cluster a down-scaled copy, scale the result back
-	int resize_on, resize_type;    // type 1: INTER_LINEAR, 3: INTER_NEAREST, 4: INTER_AREA by exactly 2 (what OpenCV makes of INTER_LINEAR at fx = 1/2)
+	int resize_on, resize_type;    // type 1: INTER_LINEAR, 2: INTER_CUBIC, 3: INTER_NEAREST, 4: INTER_AREA by exactly 2 (what OpenCV makes of INTER_LINEAR at fx = 1/2)
 	int Hs, Ws, WSs;               // small size and its shared-memory row stride
 	double factor;
 	const int16_t *rz;             // coefficient tables, offsets below (int16 entries)
 	int rz_dx, rz_dy, rz_ux, rz_uy, rz_nx, rz_ny;   // down x/y: idx,a0,a1 ; up x/y: idx,a0,a1 ; nearest x/y: idx
+	int rz_cx, rz_cy;                               // cubic down x/y: idx, w0..w3
 	// params
 	int t_threshold, clust_filt, mcs, min_samples, select_sum, op_close, com_km;
 	// split pipeline (front -> prim_kernel -> back): per-point scratch in HBM, addressed by a per-map point offset
@@ -757,6 +758,35 @@ __device__ __forceinline__ void cv_resize_linear_u8(const uint8_t *src, int sH, 
 	}
 }
 
+// cv2.resize(..., INTER_CUBIC) for uint8 (OpenCV resize.cpp): 4 taps with replicated borders, weights scaled by 2048;
+// horizontal pass in int, vertical pass in float32 as VResizeCubicVec_32s8u does it -- S0*b0 + (S1*b1 + (S2*b2 + S3*b3)),
+// every product and sum rounded separately (no FMA), b = weight / 2^22 -- then round half to even and saturate.
+__device__ __forceinline__ void cv_resize_cubic_u8(const uint8_t *src, int sH, int sW, int sstride, uint8_t *dst, int dH,
+													int dW, int dstride, const int16_t *tx, const int16_t *ty, int NT) {
+	// tx: idx[dW], w0[dW] .. w3[dW]; ty: idx[dH], w0[dH] .. w3[dH]
+	for (int i = threadIdx.x; i < dH * dW; i += NT) {
+		const int y = i / dW, x = i - y * dW;
+		const int xi = tx[x], yi = ty[y];
+		int xs[4], aw[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			xs[k] = min(max(xi - 1 + k, 0), sW - 1);
+			aw[k] = tx[(1 + k) * dW + x];
+		}
+		float acc = 0.f;
+#pragma unroll
+		for (int k = 3; k >= 0; --k) {
+			const uint8_t *row = src + min(max(yi - 1 + k, 0), sH - 1) * sstride;
+			const int r = (int)row[xs[0]] * aw[0] + (int)row[xs[1]] * aw[1] + (int)row[xs[2]] * aw[2] + (int)row[xs[3]] * aw[3];
+			const float b = __fmul_rn((float)ty[(1 + k) * dH + y], 1.f / 4194304.f);
+			const float pr = __fmul_rn((float)r, b);
+			acc = (k == 3) ? pr : __fadd_rn(pr, acc);
+		}
+		const int v = __float2int_rn(acc);
+		dst[y * dstride + x] = (uint8_t)min(max(v, 0), 255);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // Streaming variant of the map stage for clust_filt == 0 (smartVidCrop.py:2354: "Skipping clustering"):
 // threshold (a2), raw mean saliency (a3) and centre of mass (a8) are one pass over the map, so there
@@ -1035,6 +1065,8 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 			__syncthreads();
 			if (a.resize_type == 1) {
 				cv_resize_linear_u8(map8, H, W, WPS, small8, a.Hs, a.Ws, a.WSs, a.rz + a.rz_dx, a.rz + a.rz_dy, NT);
+			} else if (a.resize_type == 2) {
+				cv_resize_cubic_u8(map8, H, W, WPS, small8, a.Hs, a.Ws, a.WSs, a.rz + a.rz_cx, a.rz + a.rz_cy, NT);
 			} else if (a.resize_type == 4) {
 				// resizeAreaFast_ (OpenCV resize.cpp), scale 2: full cells (sum + 2) >> 2; the partial cells of an odd size
 				// saturate_cast<uchar>(float(sum) / count) = round half to even

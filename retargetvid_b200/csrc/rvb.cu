@@ -109,6 +109,7 @@ struct rvb_ctx {
 	DevBuf phase;
 	bool chain_levels = true;   // cut-adjacent chains go through the split pipeline, one depth per set, on the side stream;
 	                            // RVB_CHAIN_MONO=1: the monolithic kernel walks them instead (the round-1 default)
+	bool chain_levels_dense = false;   // RVB_CHAIN_LEVELS=1: also with the all-pairs Prim (slower: 3 more sets of 11 small launches)
 	int prim_variant[4] = {0, 0, 0, 0};
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
 	DevBuf maps_in, maps_nhw, filt, filt_hwn, meta, mapout, series, scratch, boxes, misc, iou_a, iou_b, iou_c;
@@ -312,6 +313,26 @@ static void linear_table(int dsize, int ssize, double scale, bool vertical, std:
 	}
 }
 
+// INTER_CUBIC (OpenCV resize.cpp): interpolateCubic with A = -0.75 in float32, weights rounded half-to-even to 1/2048.
+// Layout: idx[dsize] (position of tap 1; taps idx - 1 .. idx + 2 are clamped by the kernel), then 4 x w[dsize].
+static void cubic_table(int dsize, double scale, std::vector<int16_t> &out) {
+	const size_t base = out.size();
+	out.resize(base + 5 * (size_t)dsize);
+	for (int d = 0; d < dsize; ++d) {
+		float x = (float)((d + 0.5) * scale - 0.5);
+		const int sidx = (int)floorf(x);
+		x -= (float)sidx;
+		const float A = -0.75f;
+		float cf[4];
+		cf[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+		cf[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+		cf[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+		cf[3] = 1.f - cf[0] - cf[1] - cf[2];
+		out[base + d] = (int16_t)sidx;
+		for (int k = 0; k < 4; ++k) out[base + (size_t)(1 + k) * dsize + d] = (int16_t)nearbyintf(cf[k] * 2048.f);
+	}
+}
+
 static void nearest_table(int dsize, int ssize, double fx, std::vector<int16_t> &out) {
 	const double ifx = 1.0 / fx;
 	for (int d = 0; d < dsize; ++d) out.push_back((int16_t)std::min((int)floor(d * ifx), ssize - 1));
@@ -319,7 +340,7 @@ static void nearest_table(int dsize, int ssize, double fx, std::vector<int16_t> 
 
 struct ResizeSetup {
 	int on = 0, Hs = 0, Ws = 0, WSs = 0;
-	int dx = 0, dy = 0, ux = 0, uy = 0, nx = 0, ny = 0;
+	int dx = 0, dy = 0, ux = 0, uy = 0, nx = 0, ny = 0, cx = 0, cy = 0;
 	std::vector<int16_t> tab;
 };
 
@@ -335,6 +356,8 @@ static void build_resize(double factor, int H, int W, ResizeSetup &r) {
 	r.uy = (int)r.tab.size(); linear_table(H, r.Hs, 1.0 / ((double)H / r.Hs), true, r.tab);
 	r.nx = (int)r.tab.size(); nearest_table(r.Ws, W, fx, r.tab);
 	r.ny = (int)r.tab.size(); nearest_table(r.Hs, H, fx, r.tab);
+	r.cx = (int)r.tab.size(); cubic_table(r.Ws, 1.0 / fx, r.tab);
+	r.cy = (int)r.tab.size(); cubic_table(r.Hs, 1.0 / fx, r.tab);
 }
 
 // sc_calc_dest_size -- smartVidCrop.py:946-977
@@ -392,6 +415,8 @@ extern "C" int rvb_ctx_create(int device, rvb_ctx **out) {
 		CU(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio));
 		e = getenv("RVB_CHAIN_MONO");
 		c->chain_levels = !(e && e[0] == '1');
+		e = getenv("RVB_CHAIN_LEVELS");
+		c->chain_levels_dense = e && e[0] == '1';
 	}
 	for (int k = 0; k < kSplitClasses; ++k) {
 		CU(cudaStreamCreateWithFlags(&c->cls_stream[k], cudaStreamNonBlocking));
@@ -645,8 +670,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	if (p->resize_factor != 1.0) {
 		if (!(p->resize_factor > 1.0))
 			return fail(RVB_ERR_UNSUPPORTED, "resize_factor=%g (up-scaling before the clustering is not built)", p->resize_factor);
-		if (p->resize_type != 1 && p->resize_type != 3)
-			return fail(RVB_ERR_UNSUPPORTED, "resize_type=%d: only bilinear (1) and nearest (3) are built", p->resize_type);
+		if (p->resize_type < 1 || p->resize_type > 3)
+			return fail(RVB_ERR_UNSUPPORTED, "resize_type=%d: bilinear (1), cubic (2) and nearest (3) are built", p->resize_type);
 	}
 	if (b->n_clips <= 0) return fail(RVB_ERR_INVALID, "n_clips=%d", b->n_clips);
 	if (b->n_ratios < 1 || b->n_ratios > RVB_MAX_RATIOS) return fail(RVB_ERR_INVALID, "n_ratios=%d", b->n_ratios);
@@ -776,7 +801,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		depth[m] = (pred[m] < 0) ? 0 : depth[m - 1] + 1;   // the predecessor of map m is map m - 1
 		max_depth = std::max(max_depth, depth[m]);
 	}
-	const bool split_chains = split && max_depth < kMaxChainDepth && c->chain_levels && !c->dense_prim;
+	// (with the all-pairs Prim the chains stay in the monolithic kernel unless RVB_CHAIN_LEVELS=1: measured 21.2 vs 17.8 ms per step)
+	const bool split_chains = split && max_depth < kMaxChainDepth && c->chain_levels && (!c->dense_prim || c->chain_levels_dense);
 	std::vector<int> work;                    // monolithic launches: chain heads (the CTA walks the chain)
 	std::vector<std::vector<int>> sets;       // split pipeline
 	if (split) sets.resize(split_chains ? 2 + max_depth : 1);
@@ -954,7 +980,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	a.cvrg_cfg = p->exit_on_low_cvrg ? (const int *)(M + o_cvrg) : nullptr;
 	a.n_ratios = R; a.labels_dbg = nullptr;
 	a.resize_on = rzs.on; a.resize_type = (p->resize_type == 1 && p->resize_factor == 2.0) ? 4 : p->resize_type; a.Hs = rzs.Hs; a.Ws = rzs.Ws; a.WSs = rzs.WSs; a.factor = p->resize_factor;
-	a.rz = (const int16_t *)(M + o_rz); a.rz_dx = rzs.dx; a.rz_dy = rzs.dy; a.rz_ux = rzs.ux; a.rz_uy = rzs.uy; a.rz_nx = rzs.nx; a.rz_ny = rzs.ny;
+	a.rz = (const int16_t *)(M + o_rz); a.rz_dx = rzs.dx; a.rz_dy = rzs.dy; a.rz_ux = rzs.ux; a.rz_uy = rzs.uy; a.rz_nx = rzs.nx; a.rz_ny = rzs.ny; a.rz_cx = rzs.cx; a.rz_cy = rzs.cy;
 	a.phase_cycles = c->phase_on ? (unsigned long long *)c->phase.p : nullptr;
 	a.t_threshold = p->t_threshold; a.clust_filt = p->clust_filt; a.mcs = p->hdbscan_min;
 	a.min_samples = p->hdbscan_min_samples; a.select_sum = p->select_sum; a.op_close = p->op_close; a.com_km = p->com_km;
@@ -1056,6 +1082,12 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 					} else {
 						// a chain set: few maps, made larger by the blend
 						a.list = (const int *)(M + o_work2) + set_list_off[set]; a.head = sc; a.list_len = sc + 1;
+						if (c->dense_prim) {
+							// the all-pairs prim_kernel stops at 4096 points: larger maps (and the rest of their chains) go to the
+							// monolithic class of 8192 points at the end of the side stream
+							a.ovf_list = ovf[3]; a.ovf_len = cnt + 2 * 4 + 1;
+							return launch_map<256, 16, kModeFront>(c, a, H, W, WPS, occupancy_grid<256, 16, kModeFront>(c, make_layout(4096, H, WPS, W, mcs, 0, true).total, ns), stream);
+						}
 					}
 					// wide front (8192 points).  What it cannot place (more points than that -> flagged by the monolithic
 					// launch, or scratch exhausted) goes to the monolithic class of 8192 points, which also walks the rest

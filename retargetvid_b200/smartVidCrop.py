@@ -108,8 +108,9 @@ def _check_supported(CP):
 	if float(CP['resize_factor']) != 1.0:
 		if not float(CP['resize_factor']) > 1.0:
 			raise NotImplementedError('resize_factor=%r: up-scaling before the clustering is not built' % CP['resize_factor'])
-		if CP['resize_type'] not in (1, 3):
-			raise NotImplementedError('resize_type=2 (cubic) is not built')
+		if CP['resize_type'] not in (1, 2, 3):
+			# (the reference then takes no branch at smartVidCrop.py:1078-1084 and clusters the full-size map)
+			raise NotImplementedError('resize_type=%r: bilinear (1), cubic (2) and nearest (3) are built' % (CP['resize_type'],))
 
 
 def _times_dict(vid_dur, t_map, t_total, ingest_times):

@@ -151,6 +151,9 @@ CLIPS = {
 	# exactly 2x: cv2.resize turns INTER_LINEAR into INTER_AREA (resize.cpp, is_area_fast); 4:3 input -> 187 x 250 maps, odd height
 	'resize_area2': (dict(seed=2020, fc=110, w_orig=480, h_orig=360, shot_starts=[60]),
 					dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=2, resize_type=1, select_sum=1), ['9:16']),
+	# clustering on a 4x down-scaled copy taken with INTER_CUBIC (resize_type 2), dominant cluster by maximum
+	'resize_cubic': (dict(seed=2021, fc=130, shot_starts=[40, 90]),
+					dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=4, resize_type=2), ['1:3', '4:5']),
 	# a different sampling table: every 3rd frame gets a map, 24 fps
 	'skip3_fr24': (dict(seed=2016, fc=150, fr=24.0, skip=3, shot_starts=[75]), {}, ['9:16']),
 }

@@ -195,6 +195,12 @@ def test_cv_resize_restatement_matches_opencv():
 			assert np.array_equal(cv2.resize(a, (W, H), interpolation=cv2.INTER_LINEAR), cv_resize.resize_linear_u8(a, dsize_wh=(W, H)))
 			assert np.array_equal(cv2.resize(m, None, fx=1.0 / f, fy=1.0 / f, interpolation=cv2.INTER_NEAREST),
 								cv_resize.resize_nearest_u8(m, 1.0 / f, 1.0 / f))
+		# INTER_CUBIC (resize_type 2, smartVidCrop.py:1081-1082) at the factors whose sampling cv2 (IPP build) shares with
+		# OpenCV's own code; the process size and odd sizes
+		for f in (4.0, 2.0, 3.0, 5.0, 1.5, 2.5):
+			if t % 2 == 0 or f in (4.0, 2.0):
+				assert np.array_equal(cv2.resize(m, None, fx=1.0 / f, fy=1.0 / f, interpolation=cv2.INTER_CUBIC),
+									cv_resize.resize_cubic_u8(m, 1.0 / f, 1.0 / f)), (H, W, f)
 		# exactly 1/2: OpenCV takes the INTER_AREA fast path for INTER_LINEAR (odd sizes have partial last cells)
 		half = cv2.resize(m, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR)
 		assert np.array_equal(half, cv_resize.resize_area2_u8(m))

@@ -308,3 +308,22 @@ def test_filtered_maps_in_the_reference_layout(engine):
 		assert rb.filtered_hwn.shape == (vd['h_process'], vd['w_process'], int(vd['fc_sel']))
 		assert np.array_equal(np.transpose(ra.filtered, (1, 2, 0)), rb.filtered_hwn)
 		assert np.array_equal(ra.boxes, rb.boxes)
+
+
+@pytest.mark.parametrize('rtype,factor', [(2, 4), (2, 2), (2, 3), (2, 5), (1, 3), (1, 5), (3, 2)])
+def test_downscaled_clustering_vs_oracle(engine, rtype, factor):
+	"""resize_factor != 1 (smartVidCrop.py:1078-1084,1158,1184): clustering on a down-scaled copy -- INTER_LINEAR (1),
+	INTER_CUBIC (2), INTER_NEAREST (3) -- scaled back with INTER_LINEAR; filtered maps and boxes equal the oracle's
+	(oracle/cv_resize.py is checked against cv2 in the CPU suite, the factor-4 paths against reference fixtures)."""
+	from oracle import sc_oracle
+	from retargetvid_b200 import smartVidCrop as svc
+	from retargetvid_b200 import synth
+	vd = synth.make_clip(9100 + 10 * rtype + factor, fc=80, shot_starts=[33])
+	CP = svc.sc_init_crop_params()
+	CP.update(dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=factor, resize_type=rtype))
+	CP['out_ratio'] = '1:3'
+	res = engine.run([vd], CP, ['1:3'], detail=True, want_filtered='hwn')[0]
+	want = sc_oracle.smart_vid_crop_oracle(vd, dict(CP))
+	bad = (res.filtered_hwn != want['smaps_filtered']).any(axis=(0, 1))
+	assert not bad.any(), 'filtered maps differ in maps %s' % np.nonzero(bad)[0].tolist()
+	assert np.array_equal(res.boxes[0], np.array(want['bbs'], dtype=np.int32))

@@ -238,7 +238,7 @@ def test_error_behaviour(engine):
 		svc.smart_vid_crop('x.mp4', CP2, save_vid=False, vid_data=synth.make_clip(2, fc=30))
 	assert ei.value.code == _cabi.RVB_ERR_CAPACITY
 	CP3 = svc.sc_init_crop_params(use_best_settings=True)
-	CP3['resize_type'] = 2     # cubic down-scaling (cv2.INTER_CUBIC, smartVidCrop.py:1081-1082): not built, must be loud
+	CP3['resize_type'] = 5     # not one of the reference's three interpolation modes (smartVidCrop.py:1078-1084): must be loud
 	with pytest.raises(NotImplementedError):
 		svc.smart_vid_crop('x.mp4', CP3, save_vid=False, vid_data=synth.make_clip(3, fc=30))
 
