@@ -757,7 +757,7 @@ def reference_arm(args, rank, world):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('--gpus', type=int, default=1)
-	ap.add_argument('--steps', type=int, default=10)
+	ap.add_argument('--steps', type=int, default=20)
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--workload', default='c3', choices=['c3', 'c5'],

@@ -163,12 +163,17 @@ int64_t rvb_ctx_launch_count(const rvb_ctx *ctx);
  * kernel) summed over the last crop_track call; valid after a synchronise */
 int rvb_ctx_last_map_kernel_ms(rvb_ctx *ctx, float *ms, int32_t *launches);
 /* split pipeline of the last crop_track call, CUDA-event times (ms) on the launching stream:
- * out = {front launches, Prim + back launches of the maps outside cut-adjacent chains (the size classes run side by
- * side on their own streams), 0, whole map pipeline incl. the joined side stream with the chains} */
+ * out = {front launches, Prim + back launches of the maps outside cut-adjacent chains (the size classes one after the
+ * other), 0, whole map pipeline incl. the joined side stream with the chains} */
 int rvb_ctx_last_stage_ms(rvb_ctx *ctx, float out[4]);
 
 /* CUDA-event time (ms) of the IoU kernel of the last rvb_iou_batch_run call (without the table upload around it) */
 int rvb_ctx_last_iou_kernel_ms(rvb_ctx *ctx, float *ms);
+
+/* host time (microseconds) the last crop_track call spent per section: {per-clip tables, packing + upload of the tables,
+ * map input (copies / transposition launches), map pipeline launches, track launches, results (host buffers: incl. the
+ * wait for the device)} -- profiling aid for latency-bound calls, no reference equivalent */
+int rvb_ctx_last_host_us(rvb_ctx *ctx, double out[6]);
 
 /* profiling aid: when enabled, the map kernel accumulates SM cycles per phase (11 phases: load, threshold+compact,
  * core distances, Prim, argsort emulation, Cartesian tree, condensed-tree BFS, fall-out, EOM+labels, rebuild+closing,

@@ -31,7 +31,7 @@ RVB_MAPS_F32_NHW = 2
 EXPORTS = ['rvb_version', 'rvb_last_error', 'rvb_ctx_create', 'rvb_ctx_destroy', 'rvb_ctx_set_stream',
 		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_ctx_last_stage_ms', 'rvb_params_default',
 		'rvb_crop_track_batch', 'rvb_iou_batch_run', 'rvb_iou_mean_from_acc', 'rvb_debug_cluster_labels',
-		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms']
+		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms', 'rvb_ctx_last_host_us']
 
 
 class RvbError(RuntimeError):
@@ -208,6 +208,11 @@ class Context(object):
 
 	def crop_track_batch(self, params, batch):
 		check(self.lib.rvb_crop_track_batch(self.handle, C.byref(params), C.byref(batch)))
+
+	def last_host_us(self):
+		out = (C.c_double * 6)()
+		check(self.lib.rvb_ctx_last_host_us(self.handle, out))
+		return [float(v) for v in out]
 
 	def iou_batch(self, batch):
 		check(self.lib.rvb_iou_batch_run(self.handle, C.byref(batch)))

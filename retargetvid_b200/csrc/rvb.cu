@@ -16,6 +16,7 @@
 
 #include "../../include/retargetvid_b200.h"
 #include "iou_kernel.cuh"
+#include <chrono>
 #include "map_kernel.cuh"
 #include "prim_kernel.cuh"
 #include "fprim_kernel.cuh"
@@ -109,6 +110,7 @@ struct rvb_ctx {
 	DevBuf phase;
 	bool chain_levels = true;   // cut-adjacent chains go through the split pipeline, one depth per set, on the side stream;
 	                            // RVB_CHAIN_MONO=1: the monolithic kernel walks them instead (the round-1 default)
+	double host_us[6] = {0, 0, 0, 0, 0, 0};   // host time of the last crop_track call by section (rvb_ctx_last_host_us)
 	bool chain_levels_dense = false;   // RVB_CHAIN_LEVELS=1: also with the all-pairs Prim (slower: 3 more sets of 11 small launches)
 	int prim_variant[4] = {0, 0, 0, 0};
 	bool split = true;   // front -> prim_kernel -> back pipeline (RVB_NO_SPLIT=1 keeps every map in the monolithic kernel)
@@ -547,6 +549,12 @@ extern "C" int rvb_ctx_last_stage_ms(rvb_ctx *c, float out[4]) {
 	return RVB_OK;
 }
 
+extern "C" int rvb_ctx_last_host_us(rvb_ctx *c, double out[6]) {
+	if (!c || !out) return fail(RVB_ERR_INVALID, "NULL argument");
+	for (int i = 0; i < 6; ++i) out[i] = c->host_us[i];
+	return RVB_OK;
+}
+
 extern "C" int rvb_ctx_phase_cycles(rvb_ctx *c, int enable, uint64_t out[16]) {
 	if (!c) return fail(RVB_ERR_INVALID, "ctx is NULL");
 	CU(cudaSetDevice(c->device));
@@ -654,13 +662,22 @@ struct H2dGate {
 std::mutex H2dGate::mu[H2dGate::kMaxDev];
 cudaEvent_t H2dGate::ev[H2dGate::kMaxDev] = {};
 
-struct Staging {  // packs the small per-call arrays into one pinned block -> one H2D copy
-	std::vector<uint8_t> bytes;
+struct Staging {  // lays the small per-call arrays out in one block: the host arrays are copied straight into pinned memory
+	struct Item { size_t off; const void *src; size_t n; };
+	std::vector<Item> items;
+	size_t size = 0;
+	// src == nullptr: device scratch of n bytes (not written by write())
 	size_t add(const void *src, size_t n) {
-		size_t off = (bytes.size() + 255) / 256 * 256;
-		bytes.resize(off + n);
-		if (src && n) memcpy(bytes.data() + off, src, n);
+		const size_t off = (size + 255) / 256 * 256;
+		size = off + n;
+		if (src && n) items.push_back({off, src, n});
 		return off;
+	}
+	// the sources must still be alive; `zero_first`: the first `bytes` bytes start as zeros (gaps and scratch included)
+	void write(void *dst, size_t bytes, bool zero_first) const {
+		if (zero_first) memset(dst, 0, bytes);
+		for (const Item &it : items)
+			if (it.off + it.n <= bytes) memcpy((uint8_t *)dst + it.off, it.src, it.n);
 	}
 };
 }  // namespace
@@ -690,6 +707,13 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const bool host = b->mem_space == RVB_MEM_HOST;
 	cudaStream_t st = c->stream;
 
+	// host time by section: 0 tables, 1 packing + upload, 2 map input, 3 map pipeline launches, 4 track launches, 5 results
+	auto t_host = std::chrono::steady_clock::now();
+	auto lap = [&](int k) {
+		const auto now = std::chrono::steady_clock::now();
+		c->host_us[k] = std::chrono::duration<double, std::micro>(now - t_host).count();
+		t_host = now;
+	};
 	// ---- metadata --------------------------------------------------------------------------------
 	const int nc = b->n_clips;
 	long long tot_maps = 0, tot_frames = 0, tot_shots = 0;
@@ -705,7 +729,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 
 	std::vector<ClipDev> clips(nc);
 	std::vector<ShotDev> shots(NS);
-	std::vector<int> frame_shot(NF), frame_clip(NF), map_clip(NM), pred(NM, -1), store(NM, -1);
+	std::vector<int> pred(NM, -1), store(NM, -1);
 	std::vector<uint8_t> chain_next(NM, 0);
 	std::vector<int> clip_final(nc * R * 3), cvrg_cfg(nc * R * 2), clip_coef(nc);
 	std::vector<FilterCoef> coefs;
@@ -721,8 +745,6 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		d.n_maps = cl.n_maps; d.n_frames = cl.n_frames; d.n_shots = cl.n_shots;
 		d.h_orig = cl.h_orig; d.w_orig = cl.w_orig; d.fr = cl.fr;
 		d.map_offset = (int)cl.map_offset; d.frame_offset = (int)cl.frame_offset; d.shot_offset = (int)cl.shot_offset;
-		for (int k = 0; k < cl.n_maps; ++k) map_clip[d.map_offset + k] = i;
-		for (int k = 0; k < cl.n_frames; ++k) frame_clip[d.frame_offset + k] = i;
 		std::vector<char> is_cut(cl.n_maps + 2, 0);
 		for (int s = 0; s < cl.n_shots; ++s) {
 			const int32_t *row = b->shots + (cl.shot_offset + s) * 4;
@@ -740,7 +762,6 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 			max_lp_doubles = std::max<long long>(max_lp_doubles, clen + 6LL * (RVB_MAX_LP_ORDER + 1));
 			sh.scratch_base = (int)scratch_doubles;
 			scratch_doubles += need;
-			for (int f = sh.f0; f <= sh.f1; ++f) frame_shot[d.frame_offset + f] = d.shot_offset + s;
 			is_cut[sh.m0] = 1;                                     // segm_cuts: shot starts ...
 			if (s == cl.n_shots - 1) is_cut[sh.m1] = 1;            // ... + the last end (smartVidCrop.py:2324-2327)
 		}
@@ -836,13 +857,12 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		split_all.insert(split_all.end(), sets[k].begin(), sets[k].end());
 	}
 
+	lap(0);
 	Staging sg;
+	// host tables first (uploaded), then device scratch (cleared on the device, never sent over the link)
 	const size_t o_clips = sg.add(clips.data(), clips.size() * sizeof(ClipDev));
 	const size_t o_shots = sg.add(shots.data(), shots.size() * sizeof(ShotDev));
 	const size_t o_ti = sg.add(b->true_inds, (size_t)NM * sizeof(int));
-	const size_t o_fshot = sg.add(frame_shot.data(), (size_t)NF * sizeof(int));
-	const size_t o_fclip = sg.add(frame_clip.data(), (size_t)NF * sizeof(int));
-	const size_t o_mclip = sg.add(map_clip.data(), (size_t)NM * sizeof(int));
 	const size_t o_pred = sg.add(pred.data(), (size_t)NM * sizeof(int));
 	const size_t o_store = sg.add(store.data(), (size_t)NM * sizeof(int));
 	const size_t o_chain = sg.add(chain_next.data(), (size_t)NM);
@@ -853,16 +873,21 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_cnt = sg.add(counters.data(), counters.size() * sizeof(int));
 	const size_t o_rz = sg.add(rzs.tab.data(), rzs.tab.size() * sizeof(int16_t));
 	const int small_bytes = rzs.on ? rzs.Hs * rzs.WSs : 0;
-	const size_t o_jumps = sg.add(nullptr, (size_t)NM * sizeof(double));
 	const size_t o_work = sg.add(work.data(), work.size() * sizeof(int));
+	const size_t o_work2 = sg.add(split_all.data(), split_all.size() * sizeof(int));
+	const size_t data_bytes = (sg.size + 255) / 256 * 256;
+	const size_t o_fshot = sg.add(nullptr, (size_t)NF * sizeof(int));    // frame -> shot, frame -> clip, map -> clip:
+	const size_t o_fclip = sg.add(nullptr, (size_t)NF * sizeof(int));    // written by index_tables_kernel
+	const size_t o_mclip = sg.add(nullptr, (size_t)NM * sizeof(int));
+	const size_t o_jumps = sg.add(nullptr, (size_t)NM * sizeof(double));
 	const size_t o_ovf1 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf2 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf3 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovf4 = sg.add(nullptr, (size_t)NM * sizeof(int));
 	const size_t o_ovfw = sg.add(nullptr, (size_t)NM * sizeof(int));   // maps the 4096-point front hands to the wide front
-	const size_t o_work2 = sg.add(split_all.data(), split_all.size() * sizeof(int));
 	const size_t o_cls = sg.add(nullptr, (size_t)kSplitClasses * n_split * sizeof(int));
 	const size_t o_scroff = sg.add(nullptr, (size_t)(split ? NM : 0) * sizeof(int));
+	const size_t o_zero0 = (sg.size + 255) / 256 * 256;                  // ---- scratch that must start as zeros
 	const size_t o_skip = sg.add(nullptr, (size_t)(split ? NM : 0));
 	const size_t o_borders = sg.add(nullptr, (size_t)nc * 4 * sizeof(int));
 	const size_t o_status = sg.add(nullptr, (size_t)nc * sizeof(int));
@@ -874,14 +899,18 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	const size_t o_empty = sg.add(nullptr, (size_t)NM);
 	const size_t o_minmax = sg.add(nullptr, (size_t)NS * 4 * sizeof(double));
 	const size_t o_nf = sg.add(nullptr, (size_t)((b->centres_nf && host) ? 2 * NM : 0) * sizeof(double));
-	const size_t meta_bytes = sg.bytes.size();
+	const size_t meta_bytes = sg.size;
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
-	if (c->stage.ensure(meta_bytes)) return RVB_ERR_CUDA;
+	if (c->stage.ensure(data_bytes)) return RVB_ERR_CUDA;
 	if (c->meta.ensure(meta_bytes)) return RVB_ERR_CUDA;
-	memcpy(c->stage.p, sg.bytes.data(), meta_bytes);
-	CU(cudaMemcpyAsync(c->meta.p, c->stage.p, meta_bytes, cudaMemcpyHostToDevice, st));
+	sg.write(c->stage.p, data_bytes, false);
+	CU(cudaMemcpyAsync(c->meta.p, c->stage.p, data_bytes, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(c->ev_stage, st));
 	c->stage_busy = true;
+	CU(cudaMemsetAsync((uint8_t *)c->meta.p + o_zero0, 0, meta_bytes - o_zero0, st));
+	index_tables_kernel<<<NS + nc, 128, 0, st>>>((const ShotDev *)((uint8_t *)c->meta.p + o_shots), NS, (const ClipDev *)((uint8_t *)c->meta.p + o_clips), nc,
+												  (int *)((uint8_t *)c->meta.p + o_fshot), (int *)((uint8_t *)c->meta.p + o_fclip), (int *)((uint8_t *)c->meta.p + o_mclip));
+	c->launches += 1;
 	uint8_t *M = (uint8_t *)c->meta.p;
 	const ClipDev *d_clips = (const ClipDev *)(M + o_clips);
 	const ShotDev *d_shots = (const ShotDev *)(M + o_shots);
@@ -893,6 +922,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	int *d_status = (int *)(M + o_status);
 	uint32_t *d_prof = (uint32_t *)(M + o_prof);
 
+	lap(1);
 	// ---- maps ------------------------------------------------------------------------------------
 	const uint8_t *d_u8 = nullptr;
 	const float *d_f32 = nullptr;
@@ -955,8 +985,8 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		gstride = WPS;
 	}
 
+	lap(2);
 	// ---- border profiles ---------------------------------------------------------------------------
-	CU(cudaMemsetAsync(d_prof, 0, (size_t)nc * (H + W) * sizeof(uint32_t), st));
 	if (p->t_border != -1) {
 		border_profile_kernel<<<NM, 128, 0, st>>>(d_u8, H, W, gstride, (const int *)(M + o_mclip), d_prof);
 		CU(cudaGetLastError());
@@ -1188,6 +1218,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	CU(cudaEventRecord(c->ev_map1, st));
 	c->map_timed = true;
 
+	lap(3);
 	// ---- centre track ------------------------------------------------------------------------------
 	// series: dx, dy [NM]; dxi, dyi, dxl, dyl, dxs, dys [NF]
 	if (c->series.ensure(((size_t)2 * NM + (size_t)6 * NF) * sizeof(double))) return RVB_ERR_CUDA;
@@ -1225,9 +1256,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 													   (const int *)(M + o_ccoef), d_dxi, d_dyi, d_dxl, d_dyl, d_scratch, p->lp_filt, lp_doubles, d_minmax,
 													   p->loess_filt, p->loess_w_secs, p->loess_degree);
 	{
-		const long long warps = 2LL * NF;
-		const int blocks = (int)((warps * 32 + 255) / 256);
-		smooth_kernel<<<blocks, 256, 0, st>>>(d_shots, d_fshot, NF, d_clips, d_dxl, d_dyl, d_dxs, d_dys, p->loess_filt,
+		smooth_kernel<<<dim3((NF + 127) / 128, 2), 128, 0, st>>>(d_shots, d_fshot, NF, d_clips, d_dxl, d_dyl, d_dxs, d_dys, p->loess_filt,
 											  p->loess_w_secs, p->loess_degree, d_minmax, d_scratch);
 	}
 	int32_t *d_dims = (int32_t *)(M + o_dims);
@@ -1238,6 +1267,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	CU(cudaGetLastError());
 	c->launches += 7;
 
+	lap(4);
 	// ---- results -----------------------------------------------------------------------------------
 	// Host buffers: a copy into pageable memory is staged by the driver and blocks the calling thread, once per array.
 	// So every output whose destination is not page-locked goes through one pinned block of the context (asynchronous
@@ -1334,6 +1364,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 							status[i] == RVB_ERR_CAPACITY ? "a map has more salient pixels than RVB_MAX_POINTS"
 														  : "no map with a salient pixel (the reference raises TypeError in interp_handler)");
 	}
+	lap(5);
 	return RVB_OK;
 }
 
@@ -1392,9 +1423,9 @@ extern "C" int rvb_iou_batch_run(rvb_ctx *c, const rvb_iou_batch *b) {
 	const size_t o_acc3 = sg.add(nullptr, (size_t)V * U * 4 * sizeof(uint64_t));
 	const size_t o_bad = sg.add(nullptr, sizeof(int));
 	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
-	if (c->stage.ensure(sg.bytes.size()) || c->iou_a.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
-	memcpy(c->stage.p, sg.bytes.data(), sg.bytes.size());
-	CU(cudaMemcpyAsync(c->iou_a.p, c->stage.p, sg.bytes.size(), cudaMemcpyHostToDevice, st));
+	if (c->stage.ensure(sg.size) || c->iou_a.ensure(sg.size)) return RVB_ERR_CUDA;
+	sg.write(c->stage.p, o_acc, false);          // (the tables; the accumulators behind them are device scratch)
+	CU(cudaMemcpyAsync(c->iou_a.p, c->stage.p, o_acc, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(c->ev_stage, st));
 	c->stage_busy = true;
 	uint8_t *M = (uint8_t *)c->iou_a.p;
@@ -1628,17 +1659,18 @@ extern "C" int rvb_debug_smooth_series(rvb_ctx *c, const rvb_params *p, const do
 	const size_t o_xs = sg.add(nullptr, (size_t)n * sizeof(double)), o_ys = sg.add(nullptr, (size_t)n * sizeof(double));
 	const size_t o_scr = sg.add(nullptr, (size_t)(2 * (n + 6 * (RVB_MAX_LP_ORDER + 1)) + 16) * sizeof(double));
 	const size_t o_mm = sg.add(nullptr, 4 * sizeof(double));
-	if (c->misc.ensure(sg.bytes.size())) return RVB_ERR_CUDA;
+	if (c->misc.ensure(sg.size)) return RVB_ERR_CUDA;
 	uint8_t *D = (uint8_t *)c->misc.p;
-	CU(cudaMemcpyAsync(D, sg.bytes.data(), sg.bytes.size(), cudaMemcpyHostToDevice, st));
+	std::vector<uint8_t> blob(sg.size);
+	sg.write(blob.data(), sg.size, true);
+	CU(cudaMemcpyAsync(D, blob.data(), sg.size, cudaMemcpyHostToDevice, st));
 	CU(cudaStreamSynchronize(st));
 	const int dbg_lp_doubles = std::min(n + 6 * (RVB_MAX_LP_ORDER + 1), 6144);
 	lowpass_kernel<<<2, 32, (size_t)dbg_lp_doubles * sizeof(double), st>>>((const ShotDev *)(D + o_sh), 1, (const ClipDev *)(D + o_cl), (const FilterCoef *)(D + o_fc),
 									  (const int *)(D + o_cc), (const double *)(D + o_x), (const double *)(D + o_y),
 									  (double *)(D + o_xl), (double *)(D + o_yl), (double *)(D + o_scr), p->lp_filt, dbg_lp_doubles, (double *)(D + o_mm),
 									  p->loess_filt, p->loess_w_secs, p->loess_degree);
-	const int blocks = (int)((2LL * n * 32 + 255) / 256);
-	smooth_kernel<<<blocks, 256, 0, st>>>((const ShotDev *)(D + o_sh), (const int *)(D + o_fs), n, (const ClipDev *)(D + o_cl),
+	smooth_kernel<<<dim3((n + 127) / 128, 2), 128, 0, st>>>((const ShotDev *)(D + o_sh), (const int *)(D + o_fs), n, (const ClipDev *)(D + o_cl),
 										  (const double *)(D + o_xl), (const double *)(D + o_yl), (double *)(D + o_xs),
 										  (double *)(D + o_ys), p->loess_filt, p->loess_w_secs, p->loess_degree, (const double *)(D + o_mm), (const double *)(D + o_scr));
 	CU(cudaGetLastError());

@@ -249,31 +249,46 @@ __global__ void __launch_bounds__(32) spline_setup_kernel(const ShotDev *shots, 
 	}
 	__syncwarp();
 	if (lane == 0) {
-		// Gaussian elimination without pivoting (the collocation matrix is totally positive).  One division per row: the
-		// reciprocal of the pivot is kept in the (dead) sub-diagonal slot band[i][0] for the back substitution.
+		// Gaussian elimination without pivoting (the collocation matrix is totally positive; two sub- and two super-
+		// diagonals).  The pivot row and the two rows below it live in registers and the next row is loaded while the
+		// current step computes, so the serial chain per row is one division and two dependent FMAs instead of a string
+		// of shared-memory round trips.  One division per row: the reciprocal of the pivot is kept in the (dead) sub-
+		// diagonal slot band[i][0] for the back substitution.
+		struct Row { double l2, l1, d, u1, u2, x, y; };
+		auto load_row = [&](int r) -> Row {
+			Row q;
+			if (r < n) {
+				q.l2 = band[r * 5 + 0]; q.l1 = band[r * 5 + 1]; q.d = band[r * 5 + 2]; q.u1 = band[r * 5 + 3]; q.u2 = band[r * 5 + 4];
+				q.x = cx[r]; q.y = cy[r];
+			} else {
+				q.l2 = 0.0; q.l1 = 0.0; q.d = 1.0; q.u1 = 0.0; q.u2 = 0.0; q.x = 0.0; q.y = 0.0;
+			}
+			return q;
+		};
+		Row r0 = load_row(0), r1 = load_row(1), r2 = load_row(2);
 		for (int i = 0; i < n; ++i) {
-			const double inv = 1.0 / band[i * 5 + 2];
+			const Row r3 = load_row(i + 3);
+			const double inv = 1.0 / r0.d;
+			const double f1 = r1.l1 * inv, f2 = r2.l2 * inv;
+			r1.d -= f1 * r0.u1; r1.u1 -= f1 * r0.u2; r1.x -= f1 * r0.x; r1.y -= f1 * r0.y;
+			r2.l1 -= f2 * r0.u1; r2.d -= f2 * r0.u2; r2.x -= f2 * r0.x; r2.y -= f2 * r0.y;
 			band[i * 5 + 0] = inv;
-			for (int r = i + 1; r <= min(n - 1, i + 2); ++r) {
-				const int o = i - r + 2;  // column i in row r
-				const double f = band[r * 5 + o] * inv;
-				if (f == 0.0) continue;
-				for (int c = i; c <= min(n - 1, i + 2); ++c) {
-					const int oi = c - i + 2, orr = c - r + 2;
-					if (orr >= 0 && orr < 5) band[r * 5 + orr] -= f * band[i * 5 + oi];
-				}
-				cx[r] -= f * cx[i];
-				cy[r] -= f * cy[i];
-			}
+			band[i * 5 + 3] = r0.u1;
+			cx[i] = r0.x;
+			cy[i] = r0.y;
+			r0 = r1; r1 = r2; r2 = r3;
 		}
+		double x1 = 0.0, x2 = 0.0, y1 = 0.0, y2 = 0.0;
+		double u1 = band[(n - 1) * 5 + 3], u2 = band[(n - 1) * 5 + 4], inv = band[(n - 1) * 5 + 0], bx = cx[n - 1], by = cy[n - 1];
 		for (int i = n - 1; i >= 0; --i) {
-			double sx = cx[i], sy = cy[i];
-			for (int c = i + 1; c <= min(n - 1, i + 2); ++c) {
-				sx -= band[i * 5 + (c - i + 2)] * cx[c];
-				sy -= band[i * 5 + (c - i + 2)] * cy[c];
-			}
-			cx[i] = sx * band[i * 5 + 0];
-			cy[i] = sy * band[i * 5 + 0];
+			const double cu1 = (i + 1 < n) ? u1 : 0.0, cu2 = (i + 2 < n) ? u2 : 0.0, cinv = inv, cbx = bx, cby = by;
+			if (i > 0) { u1 = band[(i - 1) * 5 + 3]; u2 = band[(i - 1) * 5 + 4]; inv = band[(i - 1) * 5 + 0]; bx = cx[i - 1]; by = cy[i - 1]; }
+			double sx = cbx, sy = cby;
+			sx -= cu1 * x1; sy -= cu1 * y1;
+			sx -= cu2 * x2; sy -= cu2 * y2;
+			sx *= cinv; sy *= cinv;
+			cx[i] = sx; cy[i] = sy;
+			x2 = x1; y2 = y1; x1 = sx; y1 = sy;
 		}
 	}
 	__syncwarp();
@@ -328,42 +343,94 @@ __global__ void interp_eval_kernel(const ShotDev *shots, const int *frame_shot, 
 // a11: sc_butter_lowpass_filter, smartVidCrop.py:1599-1627: scipy.signal.filtfilt (odd padding of
 // 3*max(len(a),len(b)) samples, lfilter_zi initial state, direct form II transposed), with the
 // reference's moving-average fallback when filtfilt raises (shots of <= padlen frames).
-// One thread per (shot, axis).
+// One warp per (shot, axis).
 // ---------------------------------------------------------------------------------------------
-// forward and backward pass of filtfilt over buf[0 .. ne), direct form II transposed, with the state and the
-// coefficients in registers (the order is a compile-time constant: no local-memory array on the serial chain)
+// forward and backward pass of filtfilt over buf[0 .. ne), direct form II transposed, by one warp.  The recurrence is
+// linear in (state, input): z' = A z + B x.  Each pass is cut into 32 chunks of L samples, one per lane:
+//   1. every lane runs its chunk from a ZERO state and keeps the end state e_k (zero-state response);
+//   2. the true state at the start of chunk k follows from s_k = A^L s_(k-1) + e_(k-1) (lane 0, 31 small matrix-vector
+//      products; the columns of A^L come from lanes 0 .. M-1 running the homogeneous recurrence on the unit vectors);
+//   3. every lane runs its chunk again from s_k and stores the outputs -- the same operations in the same order as the
+//      sequential filter, only the chunk's start state carries different rounding (relative 1e-16).
+// 2 640 serial steps of the longest shot become 3 x 83 + 31.  State and coefficients stay in registers (the order is a
+// compile-time constant).
+struct FiltScratch { double P[8][8], E[32][8], S[32][8]; };
+
 template <int M>
-__device__ __forceinline__ void filtfilt_inplace(const FilterCoef &fc, double *buf, int ne) {
-	double b[M + 1], a[M + 1], zi[M], z[M];
+__device__ __forceinline__ void filtfilt_warp(const FilterCoef &fc, double *buf, int ne, int lane, FiltScratch &fs) {
+	double b[M + 1], a[M + 1];
 #pragma unroll
 	for (int i = 0; i <= M; ++i) { b[i] = fc.b[i]; a[i] = fc.a[i]; }
-#pragma unroll
-	for (int i = 0; i < M; ++i) zi[i] = fc.zi[i];
-	auto step = [&](double x) -> double {
+	auto step = [&](double (&z)[M], double x) -> double {
 		const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
 #pragma unroll
 		for (int i = 0; i < M - 1; ++i) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(x, b[i + 1])), __dmul_rn(y, a[i + 1]));
 		z[M - 1] = __dsub_rn(__dmul_rn(x, b[M]), __dmul_rn(y, a[M]));
 		return y;
 	};
-	// (the next sample is loaded before the current one enters the serial chain)
-	const double e0 = buf[0];
+	const int L = (ne + 31) >> 5;
+	if (lane < M) {
+		double z[M];
 #pragma unroll
-	for (int i = 0; i < M; ++i) z[i] = zi[i] * e0;
-	double xn = e0;
-	for (int i = 0; i < ne; ++i) {
-		const double xc = xn;
-		if (i + 1 < ne) xn = buf[i + 1];
-		buf[i] = step(xc);
+		for (int i = 0; i < M; ++i) z[i] = (i == lane) ? 1.0 : 0.0;
+		for (int n = 0; n < L; ++n) step(z, 0.0);
+#pragma unroll
+		for (int r = 0; r < M; ++r) fs.P[r][lane] = z[r];
 	}
-	const double y0 = buf[ne - 1];
+	const int i0 = min(ne, lane * L), i1 = min(ne, i0 + L);
+	for (int pass = 0; pass < 2; ++pass) {
+		const int dir = pass ? -1 : 1;
+		double *p0 = pass ? (buf + ne - 1 - i0) : (buf + i0);       // first sample of this lane's chunk in pass order
+		double z[M];
 #pragma unroll
-	for (int i = 0; i < M; ++i) z[i] = zi[i] * y0;
-	xn = y0;
-	for (int i = ne - 1; i >= 0; --i) {
-		const double xc = xn;
-		if (i > 0) xn = buf[i - 1];
-		buf[i] = step(xc);
+		for (int i = 0; i < M; ++i) z[i] = 0.0;
+		{
+			// (the next sample is loaded before the current one enters the serial chain)
+			const double *q = p0;
+			double xn = (i0 < i1) ? *q : 0.0;
+			for (int i = i0; i < i1; ++i) {
+				const double xc = xn;
+				q += dir;
+				if (i + 1 < i1) xn = *q;
+				step(z, xc);
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < M; ++r) fs.E[lane][r] = z[r];
+		__syncwarp();
+		if (lane == 0) {
+			double sv[M];
+			const double x0 = pass ? buf[ne - 1] : buf[0];          // filtfilt: lfilter_zi state scaled by the first sample
+#pragma unroll
+			for (int r = 0; r < M; ++r) { sv[r] = fc.zi[r] * x0; fs.S[0][r] = sv[r]; }
+			for (int k = 1; k < 32; ++k) {
+				double t[M];
+#pragma unroll
+				for (int r = 0; r < M; ++r) {
+					double acc = fs.E[k - 1][r];
+#pragma unroll
+					for (int c = 0; c < M; ++c) acc += fs.P[r][c] * sv[c];
+					t[r] = acc;
+				}
+#pragma unroll
+				for (int r = 0; r < M; ++r) { sv[r] = t[r]; fs.S[k][r] = t[r]; }
+			}
+		}
+		__syncwarp();
+#pragma unroll
+		for (int r = 0; r < M; ++r) z[r] = fs.S[lane][r];
+		{
+			double *q = p0;
+			double xn = (i0 < i1) ? *q : 0.0;
+			for (int i = i0; i < i1; ++i) {
+				const double xc = xn;
+				double *cur = q;
+				q += dir;
+				if (i + 1 < i1) xn = *q;
+				*cur = step(z, xc);
+			}
+		}
+		__syncwarp();
 	}
 }
 
@@ -374,6 +441,7 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 													  double *scratch, int lp_filt, int smem_doubles, double *shot_minmax,
 													  int loess_filt, double loess_w_secs, int degree) {
 	extern __shared__ double lp_smem[];
+	__shared__ FiltScratch lp_fs;
 	const int id = blockIdx.x, lane = threadIdx.x;
 	if (id >= n_shots * 2) return;
 	const int s = id >> 1, axis = id & 1;
@@ -388,7 +456,7 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 	if (!lp_filt) {
 		for (int i = lane; i < cl; i += 32) { const double v = x[i]; out[i] = v; vmin = fmin(vmin, v); vmax = fmax(vmax, v); }
 	} else if (m > 0 && cl > edge) {
-		// odd extension (lanes in parallel), forward pass in place, backward pass in place (lane 0), copy out
+		// odd extension (lanes in parallel), forward and backward pass in place (filtfilt_warp), copy out
 		const int ne = cl + 2 * edge;
 		double *buf = (ne <= smem_doubles) ? lp_smem : (scratch + sh.scratch_base + (size_t)axis * ne);
 		for (int i = lane; i < ne; i += 32) {
@@ -399,17 +467,15 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 			buf[i] = v;
 		}
 		__syncwarp();
-		if (lane == 0) {
-			switch (m) {
-			case 1: filtfilt_inplace<1>(fc, buf, ne); break;
-			case 2: filtfilt_inplace<2>(fc, buf, ne); break;
-			case 3: filtfilt_inplace<3>(fc, buf, ne); break;
-			case 4: filtfilt_inplace<4>(fc, buf, ne); break;
-			case 5: filtfilt_inplace<5>(fc, buf, ne); break;
-			case 6: filtfilt_inplace<6>(fc, buf, ne); break;
-			case 7: filtfilt_inplace<7>(fc, buf, ne); break;
-			default: filtfilt_inplace<8>(fc, buf, ne); break;
-			}
+		switch (m) {
+		case 1: filtfilt_warp<1>(fc, buf, ne, lane, lp_fs); break;
+		case 2: filtfilt_warp<2>(fc, buf, ne, lane, lp_fs); break;
+		case 3: filtfilt_warp<3>(fc, buf, ne, lane, lp_fs); break;
+		case 4: filtfilt_warp<4>(fc, buf, ne, lane, lp_fs); break;
+		case 5: filtfilt_warp<5>(fc, buf, ne, lane, lp_fs); break;
+		case 6: filtfilt_warp<6>(fc, buf, ne, lane, lp_fs); break;
+		case 7: filtfilt_warp<7>(fc, buf, ne, lane, lp_fs); break;
+		default: filtfilt_warp<8>(fc, buf, ne, lane, lp_fs); break;
 		}
 		__syncwarp();
 		for (int i = lane; i < cl; i += 32) { const double v = buf[edge + i]; out[i] = v; vmin = fmin(vmin, v); vmax = fmax(vmax, v); }
@@ -465,11 +531,10 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 }
 
 // ---------------------------------------------------------------------------------------------
-// a12: loess_handler + pyloess.Loess.estimate (pyloess.py:61-95), one output frame per warp.
+// a12: loess_handler + pyloess.Loess.estimate (pyloess.py:61-95), one output frame per thread.
 // The reference fits, for every frame j, a tricube-weighted polynomial over the `window` nearest
 // frames and evaluates it at j.  Here the fit is done in coordinates centred on j (u = i - j), so the
-// estimate is the constant coefficient; lanes stride the window, the moment sums are reduced with
-// shuffles and lane 0 solves the 3x3 (or 2x2) normal equations.  Savitzky-Golay (loess_filt == 0,
+// estimate is the constant coefficient: moment sums over the window, then the 3x3 (or 2x2) normal equations.  Savitzky-Golay (loess_filt == 0,
 // scipy.signal.savgol_filter mode='interp') is the same fit with unit weights.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -478,21 +543,24 @@ __device__ __forceinline__ double warp_sum(double v) {
 	return v;
 }
 
-__global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n_frames_total, const ClipDev *clips,
+__global__ void __launch_bounds__(128) smooth_kernel(const ShotDev *shots, const int *frame_shot, int n_frames_total, const ClipDev *clips,
 							  const double *dxl, const double *dyl, double *dxs, double *dys, int loess_filt,
 							  double loess_w_secs, int degree, const double *shot_minmax, const double *scratch) {
-	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	if (gw >= n_frames_total * 2) return;
-	const int f = gw >> 1, axis = gw & 1;
+	// one thread per (frame, axis = blockIdx.y): consecutive threads read consecutive samples; the frames of a shot whose
+	// window is clamped (the first and last (window - 1) / 2) sit next to each other, so a warp is almost always all
+	// interior (fixed coefficients, one FMA per tap) or all edge (moment sums + 3x3 solve)
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	const int axis = blockIdx.y;
+	if (f >= n_frames_total) return;
 	const int shot = frame_shot[f];
 	const ShotDev sh = shots[shot];
 	const int cl = sh.f1 - sh.f0 + 1;
 	const int j = f - sh.frame_base;
 	const double *y = (axis ? dyl : dxl) + sh.frame_base;
 	double *out = (axis ? dys : dxs) + sh.frame_base;
+	const double yj = y[j];
 	if (cl < 10) {  // loess_handler: short shots bypass smoothing
-		if (lane == 0) out[j] = y[j];
+		out[j] = yj;
 		return;
 	}
 	const double fr = clips[sh.clip].fr;
@@ -506,22 +574,28 @@ __global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n
 	// come from the low-pass kernel.
 	const double ymin = shot_minmax[((size_t)shot * 2 + axis) * 2], ymax = shot_minmax[((size_t)shot * 2 + axis) * 2 + 1];
 	if (loess_filt && !(ymax > ymin)) {
-		if (lane == 0) out[j] = y[j];
+		out[j] = yj;
 		return;
 	}
 	if (h >= 1 && j - h >= 0 && j + h <= cl - 1) {
-		// window not clamped: fixed coefficients (lowpass_kernel)
+		// window not clamped: fixed coefficients (lowpass_kernel); four partial sums keep the FMA chains short
 		const double *coef = scratch + sh.scratch_base;
-		const double yj = y[j];
-		double acc = 0.0;
-		for (int i = lane; i < win; i += 32) acc += coef[i] * (y[lo + i] - yj);
-		acc = warp_sum(acc);
-		if (lane == 0) out[j] = acc + yj;
+		const double *yw = y + lo;
+		double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+		int i = 0;
+		for (; i + 3 < win; i += 4) {
+			a0 += coef[i] * (yw[i] - yj);
+			a1 += coef[i + 1] * (yw[i + 1] - yj);
+			a2 += coef[i + 2] * (yw[i + 2] - yj);
+			a3 += coef[i + 3] * (yw[i + 3] - yj);
+		}
+		for (; i < win; ++i) a0 += coef[i] * (yw[i] - yj);
+		out[j] = ((a0 + a1) + (a2 + a3)) + yj;
 		return;
 	}
 	const double dmax = (double)max(j - lo, lo + win - 1 - j);
 	double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, t0 = 0, t1 = 0, t2 = 0;
-	for (int i = lo + lane; i < lo + win; i += 32) {
+	for (int i = lo; i < lo + win; ++i) {
 		const double u = (double)(i - j) / dmax;  // |u| <= 1 keeps the normal equations well scaled
 		double w = 1.0;
 		if (loess_filt) {
@@ -529,28 +603,24 @@ __global__ void smooth_kernel(const ShotDev *shots, const int *frame_shot, int n
 			const double c = 1.0 - r * r * r;
 			w = c * c * c;
 		}
-		const double yy = y[i] - y[j];
+		const double yy = y[i] - yj;
 		const double wu = w * u, wu2 = wu * u;
 		s0 += w; s1 += wu; s2 += wu2; s3 += wu2 * u; s4 += wu2 * u * u;
 		t0 += w * yy; t1 += wu * yy; t2 += wu2 * yy;
 	}
-	s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3); s4 = warp_sum(s4);
-	t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
-	if (lane == 0) {
-		double b0;
-		if (degree >= 2) {
-			// solve [s0 s1 s2; s1 s2 s3; s2 s3 s4] b = [t0 t1 t2] for b0 (Cramer, symmetric 3x3)
-			const double c00 = s2 * s4 - s3 * s3;
-			const double c01 = s1 * s4 - s2 * s3;
-			const double c02 = s1 * s3 - s2 * s2;
-			const double det = s0 * c00 - s1 * c01 + s2 * c02;
-			b0 = (t0 * c00 - t1 * c01 + t2 * c02) / det;
-		} else {
-			const double det = s0 * s2 - s1 * s1;
-			b0 = (t0 * s2 - t1 * s1) / det;
-		}
-		out[j] = b0 + y[j];
+	double b0;
+	if (degree >= 2) {
+		// solve [s0 s1 s2; s1 s2 s3; s2 s3 s4] b = [t0 t1 t2] for b0 (Cramer, symmetric 3x3)
+		const double c00 = s2 * s4 - s3 * s3;
+		const double c01 = s1 * s4 - s2 * s3;
+		const double c02 = s1 * s3 - s2 * s2;
+		const double det = s0 * c00 - s1 * c01 + s2 * c02;
+		b0 = (t0 * c00 - t1 * c01 + t2 * c02) / det;
+	} else {
+		const double det = s0 * s2 - s1 * s1;
+		b0 = (t0 * s2 - t1 * s1) / det;
 	}
+	out[j] = b0 + yj;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -689,6 +759,25 @@ __global__ void __launch_bounds__(128) clip_scores_kernel(const ClipDev *clips, 
 			for (int i = 0; i < cl.n_maps; ++i)
 				for (int r = 0; r < n_ratios; ++r) cv[r] += mo[cl.map_offset + i].cvrg[r];
 		for (int r = 0; r < n_ratios; ++r) out[1 + r] = cv[r] / (double)cl.n_maps;
+	}
+}
+
+// frame -> shot, frame -> clip and map -> clip tables, from the shot and clip descriptors (blocks 0 .. n_shots - 1: one
+// shot each; the following n_clips blocks: the maps of one clip each).  Built on the device: 8 bytes per frame that the
+// host neither fills nor sends.
+__global__ void __launch_bounds__(128) index_tables_kernel(const ShotDev *__restrict__ shots, int n_shots, const ClipDev *__restrict__ clips, int n_clips,
+															 int *__restrict__ frame_shot, int *__restrict__ frame_clip, int *__restrict__ map_clip) {
+	const int b = blockIdx.x;
+	if (b < n_shots) {
+		const ShotDev sh = shots[b];
+		const int n = sh.f1 - sh.f0 + 1;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) {
+			frame_shot[sh.frame_base + i] = b;
+			frame_clip[sh.frame_base + i] = sh.clip;
+		}
+	} else {
+		const ClipDev cd = clips[b - n_shots];
+		for (int i = threadIdx.x; i < cd.n_maps; i += blockDim.x) map_clip[cd.map_offset + i] = b - n_shots;
 	}
 }
 

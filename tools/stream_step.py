@@ -30,3 +30,17 @@ for _ in range(10):
 e1.record(st)
 torch.cuda.synchronize()
 print('streaming step %.3f ms (%d maps, %d frames)' % (e0.elapsed_time(e1) / 10, wl.NM, wl.NF))
+import time  # noqa: E402
+t0 = time.perf_counter()
+for _ in range(10):
+	ctx.crop_track_batch(p, wl.b_dev[0])
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print('host time per call %.3f ms; sections (us): tables, pack+upload, map input, map launches, track launches, results = %s'
+	% ((t1 - t0) * 100, ['%.0f' % v for v in ctx.last_host_us()]))
+CP['clust_filt'] = True
+p2 = _cabi.params_from_crop_params(CP)
+for _ in range(3):
+	ctx.crop_track_batch(p2, wl.b_dev[0])
+torch.cuda.synchronize()
+print('default pipeline, host sections (us): %s' % ['%.0f' % v for v in ctx.last_host_us()])
