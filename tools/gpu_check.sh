@@ -1,6 +1,7 @@
 #!/bin/bash
 # One GPU-box visit.  Everything lands in gpurun_out/<tag>_*.
-#   tools/gpu_check.sh TAG            parity tests, smoke, bench line, ncu launch list of one bench command
+#   tools/gpu_check.sh TAG            parity tests, smoke, bench line, ncu launch list of one bench command, launch list of
+#                                     the streaming (clust_filt=False) step, single-clip latency
 #   tools/gpu_check.sh TAG full       + `ncu --set full` of ONE step's map-pipeline launches, exported to CSV on the box
 #                                       (the .ncu-rep is too large to travel) and summarised into
 #                                       gpurun_out/<tag>_map_kernel_traffic.json (copy to profiles/map_kernel_traffic.json)
@@ -17,6 +18,9 @@ tail -c 2500 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv \
 	python bench.py --steps 2 --warmup 3 --streams 1 --cpu-sample 0 --c5-clips 0 > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "launch list exit $?"; wc -l $OUT/${TAG}_launches.csv
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'map_stream|fill_centres|spline|interp_eval|lowpass|smooth|boxes_kernel|clip_scores|index_tables|border' -c 120 --csv \
+	--log-file $OUT/${TAG}_stream_launches.csv python tools/stream_step.py > $OUT/${TAG}_stream.log 2>&1
+python tools/lat_single.py > $OUT/${TAG}_lat.log 2>&1; head -4 $OUT/${TAG}_lat.log
 if [ "$2" = "full" ]; then
 	timeout 900 ncu --set full --clock-control none -k regex:'map_kernel|prim_kernel' -s 32 -c 16 -o /tmp/${TAG}_full -f \
 		python bench.py --steps 1 --warmup 3 --streams 1 --cpu-sample 0 --c5-clips 0 > $OUT/${TAG}_ncu_full.log 2>&1
