@@ -690,7 +690,9 @@ def gpu_arm(args, rank, world, local_rank):
 					'input_bytes_per_gpu': NM * H * WPS, 'l2': 'inputs larger than L2 (no flush needed)',
 					'value_entry': 'device-resident uint8 [N][140][256]', 'e2e_entry': 'pinned host uint8 [H][W][N] per clip',
 					'batches_in_flight': NCTX,
-					'counting': 'source frames per second; rounds before r02 counted frames x ratios (2x these figures for 2 ratios)'},
+					'counting': 'source frames per second; rounds before r02 counted frames x ratios (2x these figures for 2 ratios)',
+					'same_config_as_cpu_arm': False,
+					'cpu_arm_difference': 'the CPU arm (cpu_baseline / --impl reference) evaluates ONE target ratio per pass over a bounded sample of the same clips, as the reference does; this arm evaluates every ratio of the workload from one pass and counts each source frame once, so the frames/s ratio understates the work done per frame and equals the maps/s ratio (maps per frame are fixed by the sampling rule)'},
 			'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(NM * H * W), 'd2h_bytes_per_step': int(R * NF * 16),
 					'ms_per_step': ms_e2e / args.steps,
 					'h2d_copy_alone_ms': h2d_ms, 'h2d_copy_alone_gbs': NM * H * W / (h2d_ms / 1e3) / 1e9,
