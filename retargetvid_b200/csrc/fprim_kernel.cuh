@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(32, 16) fprim_kernel(const FPrimArgs a) {
 	__shared__ uint32_t uq[32 * kFrUpd];      // per lane: the key updates of its batch node, (old level << 24) | (level << 16) | point
 	__shared__ uint16_t sel[kFrBatch];        // the batch: lowest members of the lowest bucket
 	const int lane = threadIdx.x;
-	const int H = a.H, W = a.W, RS = a.RS, RSO = a.RS + 2;
+	const int H = a.H, RS = a.RS, RSO = a.RS + 2;
 	uint32_t *occ = reinterpret_cast<uint32_t *>(fsm);
 	uint16_t *wbase = reinterpret_cast<uint16_t *>(fsm + H * RS * 4);
 	const int o_pk = (H * RS * 4 + (((H * RS * 2) + 15) & ~15) + 15) & ~15;
