@@ -202,6 +202,15 @@ double rvb_iou_mean_from_acc(const uint64_t acc[2], int64_t n);
 int rvb_crop_frames(rvb_ctx *ctx, const uint8_t *frames, int32_t n_frames, int32_t h, int32_t w, int32_t channels,
                     const int32_t *boxes, int32_t out_h, int32_t out_w, uint8_t *out, int32_t mem_space);
 
+/* a16 and its reader, host code (no context): the text format of the result files -- '%d,%d,%d,%d\n' per frame
+ * (smartVidCrop.py:2783-2785), read back as int(c[0]) .. int(c[3]) of line.split(',') (retargetvid_eval.py:152-159).
+ * rvb_format_boxes_txt: boxes HOST int32 [n_frames][4] -> text; `out` needs 48 bytes per frame; *len_out = bytes written.
+ * rvb_parse_boxes_txt: text of `len` bytes -> boxes (capacity cap_frames); *n_frames_out = lines parsed.  A line that
+ * Python's int() / indexing would reject (fewer than 4 fields, an empty or non-integer field) is RVB_ERR_INVALID with
+ * the line number in rvb_last_error(); more lines than cap_frames: RVB_ERR_CAPACITY with *n_frames_out = lines present. */
+int rvb_format_boxes_txt(const int32_t *boxes, int64_t n_frames, char *out, int64_t cap, int64_t *len_out);
+int rvb_parse_boxes_txt(const char *text, int64_t len, int32_t *boxes, int64_t cap_frames, int64_t *n_frames_out);
+
 /* stage-level entry points used by the parity tests (device work only) */
 /* sc_clustering_filt on one uint8 map in host memory -- smartVidCrop.py:1062-1161 */
 int rvb_debug_cluster_labels(rvb_ctx *ctx, const rvb_params *p, const uint8_t *map_hw, int32_t h, int32_t w,

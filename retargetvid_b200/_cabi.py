@@ -31,7 +31,7 @@ RVB_MAPS_F32_NHW = 2
 EXPORTS = ['rvb_version', 'rvb_last_error', 'rvb_ctx_create', 'rvb_ctx_destroy', 'rvb_ctx_set_stream',
 		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_ctx_last_stage_ms', 'rvb_params_default',
 		'rvb_crop_track_batch', 'rvb_iou_batch_run', 'rvb_iou_mean_from_acc', 'rvb_debug_cluster_labels',
-		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms', 'rvb_ctx_last_host_us']
+		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms', 'rvb_ctx_last_host_us', 'rvb_format_boxes_txt', 'rvb_parse_boxes_txt']
 
 
 class RvbError(RuntimeError):
@@ -112,8 +112,33 @@ def load_library():
 	lib.rvb_ctx_last_iou_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
 	lib.rvb_crop_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
 									C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+	lib.rvb_ctx_last_host_us.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+	lib.rvb_format_boxes_txt.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+	lib.rvb_parse_boxes_txt.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
 	_lib = lib
 	return lib
+
+
+def format_boxes_txt(boxes):
+	"""[F, 4] boxes -> the bytes of a result file, '%d,%d,%d,%d\\n' per frame (smartVidCrop.py:2783-2785)."""
+	lib = load_library()
+	bb = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+	buf = C.create_string_buffer(max(1, 48 * len(bb)))
+	n = C.c_int64()
+	check(lib.rvb_format_boxes_txt(bb.ctypes.data, len(bb), buf, len(buf), C.byref(n)))
+	return buf.raw[:n.value]
+
+
+def parse_boxes_txt(text):
+	"""The text of a result / annotation file -> int32 [F, 4], as retargetvid_eval.py:152-159 reads it; a line that
+	int() or the indexing would reject raises RvbError naming the line."""
+	lib = load_library()
+	data = text.encode() if isinstance(text, str) else bytes(text)
+	cap = data.count(b'\n') + data.count(b'\r') + 1
+	out = np.empty((cap, 4), dtype=np.int32)
+	n = C.c_int64()
+	check(lib.rvb_parse_boxes_txt(data, len(data), out.ctypes.data, cap, C.byref(n)))
+	return out[:n.value].copy()
 
 
 def check(code):

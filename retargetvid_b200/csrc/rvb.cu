@@ -1533,6 +1533,73 @@ extern "C" double rvb_iou_mean_from_acc(const uint64_t acc[2], int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // renderer crop
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// a16: result text format (host)
+// ---------------------------------------------------------------------------------------------
+extern "C" int rvb_format_boxes_txt(const int32_t *boxes, int64_t n_frames, char *out, int64_t cap, int64_t *len_out) {
+	if (!boxes || !out || !len_out || n_frames < 0) return fail(RVB_ERR_INVALID, "NULL argument");
+	if (cap < n_frames * 48) return fail(RVB_ERR_CAPACITY, "rvb_format_boxes_txt: %lld bytes for %lld frames (48 per frame)", (long long)cap, (long long)n_frames);
+	char *q = out;
+	for (int64_t f = 0; f < n_frames; ++f) {
+		for (int k = 0; k < 4; ++k) {
+			long long v = boxes[f * 4 + k];
+			if (v < 0) { *q++ = '-'; v = -v; }
+			char tmp[12];
+			int nd = 0;
+			do { tmp[nd++] = (char)('0' + v % 10); v /= 10; } while (v);
+			while (nd) *q++ = tmp[--nd];
+			*q++ = (k < 3) ? ',' : '\n';
+		}
+	}
+	*len_out = q - out;
+	return RVB_OK;
+}
+
+extern "C" int rvb_parse_boxes_txt(const char *text, int64_t len, int32_t *boxes, int64_t cap_frames, int64_t *n_frames_out) {
+	if (!text || !n_frames_out || len < 0 || (cap_frames > 0 && !boxes)) return fail(RVB_ERR_INVALID, "NULL argument");
+	auto is_space = [](char ch) { return ch == ' ' || ch == '\t' || ch == '\v' || ch == '\f'; };
+	int64_t n = 0, pos = 0;
+	bool overflow = false;
+	while (pos < len) {
+		// one line: up to '\n', '\r' or '\r\n' (str.splitlines)
+		int64_t e = pos;
+		while (e < len && text[e] != '\n' && text[e] != '\r') ++e;
+		int64_t p = pos;
+		int32_t v4[4];
+		for (int k = 0; k < 4; ++k) {
+			// int(field): optional blanks, optional sign, digits, optional blanks
+			while (p < e && is_space(text[p])) ++p;
+			bool neg = false;
+			if (p < e && (text[p] == '+' || text[p] == '-')) { neg = text[p] == '-'; ++p; }
+			long long v = 0;
+			int nd = 0;
+			while (p < e && text[p] >= '0' && text[p] <= '9') {
+				v = v * 10 + (text[p] - '0');
+				if (v > 0x7fffffffLL + 1) return fail(RVB_ERR_INVALID, "line %lld: a coordinate does not fit 32 bits", (long long)n + 1);
+				++p; ++nd;
+			}
+			while (p < e && is_space(text[p])) ++p;
+			const bool field_end = (p == e) || text[p] == ',';
+			if (nd == 0 || !field_end) return fail(RVB_ERR_INVALID, "line %lld: field %d is not an integer", (long long)n + 1, k);
+			if (k < 3) {
+				if (p == e) return fail(RVB_ERR_INVALID, "line %lld: %d field(s), 4 needed", (long long)n + 1, k + 1);
+				++p;   // the comma
+			}
+			v = neg ? -v : v;
+			if (v > 0x7fffffffLL || v < -0x7fffffffLL - 1) return fail(RVB_ERR_INVALID, "line %lld: a coordinate does not fit 32 bits", (long long)n + 1);
+			v4[k] = (int32_t)v;
+		}
+		// (further fields are ignored, as c[4:] is)
+		if (n < cap_frames) memcpy(boxes + n * 4, v4, sizeof(v4)); else overflow = true;
+		++n;
+		pos = e;
+		if (pos < len) pos += (text[pos] == '\r' && pos + 1 < len && text[pos + 1] == '\n') ? 2 : 1;
+	}
+	*n_frames_out = n;
+	if (overflow) return fail(RVB_ERR_CAPACITY, "rvb_parse_boxes_txt: %lld lines, room for %lld", (long long)n, (long long)cap_frames);
+	return RVB_OK;
+}
+
 extern "C" int rvb_crop_frames(rvb_ctx *c, const uint8_t *frames, int32_t n_frames, int32_t h, int32_t w, int32_t channels,
 							   const int32_t *boxes, int32_t out_h, int32_t out_w, uint8_t *out, int32_t mem_space) {
 	if (!c || !frames || !boxes || !out) return fail(RVB_ERR_INVALID, "NULL argument");

@@ -24,8 +24,8 @@ ARS = ['1-3', '3-1']
 
 
 def _parse_boxes(text):
-	rows = [l.split(',') for l in text.splitlines()]
-	return np.array([[int(c[0]), int(c[1]), int(c[2]), int(c[3])] for c in rows], dtype=np.int32).reshape(-1, 4)
+	"""One box per line, int(c[0]) .. int(c[3]) of line.split(',') (retargetvid_eval.py:152-159): the library's parser."""
+	return _cabi.parse_boxes_txt(text)
 
 
 def load_annotations(annotations_dir, n_users=6):

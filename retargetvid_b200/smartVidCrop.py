@@ -333,8 +333,8 @@ def write_result_files(results_out, suffix, vid_data, info_dict):
 			stfp.write(k + ':' + str(info_dict[k]) + '\n')
 	if 'bbs' not in vid_data:
 		return      # padded: "Bounding boxes are not available" (smartVidCrop.py:2788-2790)
-	with open(os.path.join(results_out, suffix + '.txt'), 'w') as bbfp:
-		bbfp.write(''.join(['%d,%d,%d,%d\n' % (bb[0], bb[1], bb[2], bb[3]) for bb in vid_data['bbs']]))
+	with open(os.path.join(results_out, suffix + '.txt'), 'wb') as bbfp:
+		bbfp.write(_cabi.format_boxes_txt(vid_data['bbs']))      # '%d,%d,%d,%d\n' per frame
 
 
 def process_pickles(pickle_paths, results_out_top, aspect_ratios_to_test=('1:3', '3:1'), crop_params=None,

@@ -296,3 +296,30 @@ def test_multi_gpu_engine_shards_and_gathers_in_input_order(monkeypatch):
 	assert max(loads) - min(loads) <= max(v['fc_sel'] for v in vds)
 	with pytest.raises(ValueError):
 		eng_mod.MultiGpuCropEngine([0, 0])
+
+
+def test_result_text_format_and_parser_match_python():
+	"""a16 (smartVidCrop.py:2783-2785) and its reader (retargetvid_eval.py:152-159): the library's formatter writes the
+	bytes '%d,%d,%d,%d\\n' % ... does, its parser returns what int(c[k]) of line.split(',') returns and rejects what
+	Python rejects (host code of the C ABI: runs without a GPU)."""
+	from retargetvid_b200 import _cabi
+	rng = np.random.default_rng(3)
+	b = rng.integers(-3000, 5000, (5000, 4)).astype(np.int32)
+	b[0] = [0, -1, 2147483647, -2147483648]
+	want = ''.join('%d,%d,%d,%d\n' % tuple(r) for r in b.tolist())
+	got = _cabi.format_boxes_txt(b)
+	assert got == want.encode()
+	assert np.array_equal(_cabi.parse_boxes_txt(got), b)
+	assert _cabi.format_boxes_txt(np.zeros((0, 4), dtype=np.int32)) == b''
+	assert _cabi.parse_boxes_txt('').shape == (0, 4)
+	# what int() accepts: blanks around a field, a plus sign, further fields, \\r\\n line ends, no newline at the end
+	text = ' 1, -2 ,+3,4,99\r\n5,6,7,8'
+	rows = [ln.split(',') for ln in text.splitlines()]
+	py = [[int(c[0]), int(c[1]), int(c[2]), int(c[3])] for c in rows]
+	assert _cabi.parse_boxes_txt(text).tolist() == py
+	# what Python rejects (IndexError / ValueError) is an error here as well, with the line number
+	for bad in ('1,2,3\n', '1,2,3,4\n\n5,6,7,8\n', '1,2,x,4\n', '1,2,3.0,4\n', '1,2,3,\n', '1 2,3,4,5\n'):
+		with pytest.raises((ValueError, IndexError)):
+			[[int(c[0]), int(c[1]), int(c[2]), int(c[3])] for c in [ln.split(',') for ln in bad.splitlines()]]
+		with pytest.raises(_cabi.RvbError):
+			_cabi.parse_boxes_txt(bad)
