@@ -976,7 +976,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		for (int i = 0; i < nc; ++i) max_maps = std::max(max_maps, clips[i].n_maps);
 		for (int z0 = 0; z0 < nc; z0 += 65535) {
 			const int nz = std::min(nc - z0, 65535);
-			dim3 grid((max_maps + kTrMaps - 1) / kTrMaps, H, nz);
+			dim3 grid(((max_maps + kTrTN - 1) / kTrTN) * ((W + kTrTX - 1) / kTrTX), H, nz);
 			transpose_hwn_kernel<<<grid, 256, 0, st>>>(src, (size_t)NM * H * W, d_clips + z0, H, W, (uint8_t *)c->maps_nhw.p, WPS);
 			c->launches += 1;
 		}

@@ -783,73 +783,98 @@ __global__ void __launch_bounds__(128) index_tables_kernel(const ShotDev *__rest
 
 // [H][W][N] (reference layout, frame index fastest) -> [N][H][WPS], every clip of the batch in one launch.
 // The clips' [H][W][n_maps] blocks are packed back to back in src_all (clip i starts at map_offset * H * W).
-// One CTA moves one image row (W pixels) of kTrMaps consecutive maps of one clip:
-//   in : per pixel a run of <= 60 bytes at an arbitrary alignment -> half a warp reads the <= 16 aligned 32-bit words that
-//        cover it and scatters the bytes into the transposed shared tile (row stride 65 words: conflict-free);
-//   out: per map 250 contiguous bytes of a 256-byte-aligned row -> 32-bit shared loads, 128-byte coalesced stores.
-// grid: x over map tiles (fastest: the tiles of one pixel row share their cache lines), y = image row, z = clip.
-constexpr int kTrMaps = 60;
-constexpr int kTrStrideW = 65;   // words per tile row (>= WPS / 4 + 1, odd)
+// One CTA moves a tile of 64 pixels of one image row x 128 consecutive maps of one clip:
+//   in : per pixel a run of <= 128 bytes at an arbitrary alignment (the runs of neighbouring pixels follow each other in
+//        memory when the tile covers all maps of the clip) -> a warp copies the <= 33 aligned 32-bit words that cover
+//        it into one shared row (33 words: conflict-free below);
+//   out: a thread takes a 4 pixel x 4 map block: four unaligned words from shared memory (two loads + a funnel shift
+//        each), a 4 x 4 byte transposition in registers (8 PRMT), four 32-bit stores -- the 8 threads of a warp that
+//        share a map write 32 consecutive bytes of its row.  ~3 instructions per byte moved (the first version scattered
+//        single bytes into a transposed tile: 34, issue-bound at 0.80 ms per 726 MB step).
+// grid: x = map tile x pixel tile (pixel tile fastest), y = image row, z = clip.
+constexpr int kTrMaps = 60;      // (tile of transpose_to_hwn_kernel)
+constexpr int kTrStrideW = 65;   // words per tile row there (>= WPS / 4 + 1, odd)
+constexpr int kTrTN = 128, kTrTX = 64, kTrRowW = 33;
 
 __global__ void __launch_bounds__(256) transpose_hwn_kernel(const uint8_t *__restrict__ src_all, size_t src_bytes,
 															const ClipDev *__restrict__ clips, int H, int W,
 															uint8_t *__restrict__ dst, int WPS) {
-	__shared__ uint32_t tile32[kTrMaps * kTrStrideW];
-	uint8_t *tile = reinterpret_cast<uint8_t *>(tile32);
+	__shared__ uint32_t S32[kTrTX * kTrRowW];
 	const ClipDev cd = clips[blockIdx.z];
 	const int N = cd.n_maps;
-	const int n0 = blockIdx.x * kTrMaps;
+	const int xtiles = (W + kTrTX - 1) / kTrTX;
+	const int n0 = ((int)blockIdx.x / xtiles) * kTrTN;
 	if (n0 >= N) return;
-	const int nb = min(kTrMaps, N - n0);
+	const int nb = min(kTrTN, N - n0);
+	const int x0 = ((int)blockIdx.x % xtiles) * kTrTX;
+	const int nx = min(kTrTX, W - x0);
 	const int y = blockIdx.y;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int half = lane >> 4, hl = lane & 15;
 	const uintptr_t lo = reinterpret_cast<uintptr_t>(src_all), hi = lo + src_bytes;
-	const uintptr_t clip0 = lo + (size_t)cd.map_offset * H * W;
-	// ---- in ----
-	for (int x0 = warp * 2; x0 < W; x0 += 16 * 4) {
-		uint32_t w[4];
-		uintptr_t seg[4];
+	const uintptr_t run0 = lo + (size_t)cd.map_offset * H * W + ((size_t)y * W + x0) * N + n0;   // run of pixel x0; + N per pixel
+	// all offsets below are 32-bit, relative to the aligned word that holds the first byte of the tile
+	const uint32_t r0 = (uint32_t)(run0 & 3);
+	const uint32_t *base32 = reinterpret_cast<const uint32_t *>(run0 - r0);
+	// the aligned words that cover the tile's runs lie inside the source buffer (always, except at its very ends)
+	const bool inside = (run0 - r0 >= lo) && (run0 + (size_t)(nx - 1) * N + nb + 3 <= hi);
+	// ---- in ----  (every load of a thread is issued before its first store: 9 independent requests in flight)
+	if (inside) {
+		auto load_word = [&](int xl, int w) -> uint32_t {
+			const uint32_t bo = r0 + (uint32_t)(xl * N);          // byte offset of the run from the aligned base
+			uint32_t v = 0;
+			if (xl < nx && 4u * (uint32_t)w < (bo & 3u) + (uint32_t)nb) v = __ldg(base32 + (bo >> 2) + (uint32_t)w);
+			return v;
+		};
+		uint32_t v8[8];
 #pragma unroll
-		for (int u = 0; u < 4; ++u) {
-			const int x = x0 + u * 16 + half;
-			seg[u] = clip0 + ((size_t)y * W + x) * N + n0;
-			const uintptr_t a = (seg[u] & ~(uintptr_t)3) + 4u * hl;
-			w[u] = 0;
-			if (x < W && a < seg[u] + nb) {
-				if (a >= lo && a + 4 <= hi) {
-					w[u] = __ldg(reinterpret_cast<const uint32_t *>(a));
-				} else {
-					for (int k = 0; k < 4; ++k)
-						if (a + k >= lo && a + k < hi) w[u] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(a + k)) << (8 * k);
-				}
+		for (int i = 0; i < 8; ++i) v8[i] = load_word(warp + 8 * i, lane);
+		const uint32_t vx = (tid < kTrTX) ? load_word(tid, 32) : 0u;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) S32[(warp + 8 * i) * kTrRowW + lane] = v8[i];
+		if (tid < kTrTX) S32[tid * kTrRowW + 32] = vx;
+	} else {
+		// a tile at the very start or end of the source buffer: byte loads, every one checked
+		for (int i = tid; i < kTrTX * kTrRowW; i += 256) {
+			const int xl = i / kTrRowW, w = i - xl * kTrRowW;
+			const uint32_t bo = r0 + (uint32_t)(xl * N);
+			uint32_t v = 0;
+			if (xl < nx && 4u * (uint32_t)w < (bo & 3u) + (uint32_t)nb) {
+				const uintptr_t a = reinterpret_cast<uintptr_t>(base32 + (bo >> 2) + (uint32_t)w);
+				for (int k = 0; k < 4; ++k)
+					if (a + k >= lo && a + k < hi) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(a + k)) << (8 * k);
 			}
-		}
-#pragma unroll
-		for (int u = 0; u < 4; ++u) {
-			const int x = x0 + u * 16 + half;
-			if (x >= W) continue;
-			const int nl0 = (int)((long long)((seg[u] & ~(uintptr_t)3) + 4u * hl) - (long long)seg[u]);   // map index of byte 0
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const int nl = nl0 + k;
-				if (nl >= 0 && nl < nb) tile[(size_t)nl * (kTrStrideW * 4) + x] = (uint8_t)(w[u] >> (8 * k));
-			}
+			S32[i] = v;
 		}
 	}
 	__syncthreads();
 	// ---- out ----
-	const int words = (W + 3) >> 2;          // the last word may carry up to 3 bytes of the padding columns
-	uint8_t *out = dst + ((size_t)(cd.map_offset + n0) * H + y) * WPS;
-	const size_t map_stride = (size_t)H * WPS;
-	for (int i = tid; i < nb * 64; i += 256) {
-		const int r = i >> 6, c = i & 63;
-		if (c < words) {
-			uint32_t v = tile32[r * kTrStrideW + c];
-			const int valid = W - 4 * c;     // bytes of this word that are pixels
-			if (valid < 4) v &= (1u << (8 * valid)) - 1u;
-			*reinterpret_cast<uint32_t *>(out + (size_t)r * map_stride + 4 * c) = v;
+	// 16 pixel quads x 32 map quads; a warp covers 8 pixel quads x 4 map quads
+#pragma unroll
+	for (int it = 0; it < 2; ++it) {
+		const int wt = warp + 8 * it;                   // 0 .. 15
+		const int xq = (wt & 1) * 8 + (lane & 7);
+		const int n4 = (wt >> 1) * 4 + (lane >> 3);
+		if (4 * n4 >= nb || 4 * xq >= nx) continue;
+		uint32_t w4[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int xl = 4 * xq + k;
+			uint32_t v = 0;
+			if (xl < nx) {
+				const int o = (int)((r0 + (uint32_t)(xl * N)) & 3u) + 4 * n4;    // byte offset inside the shared row
+				const uint32_t *row = S32 + xl * kTrRowW + (o >> 2);
+				v = __funnelshift_r(row[0], row[1], (o & 3) * 8);
+			}
+			w4[k] = v;
 		}
+		const uint32_t t0 = __byte_perm(w4[0], w4[1], 0x5140), t1 = __byte_perm(w4[2], w4[3], 0x5140);
+		const uint32_t t2 = __byte_perm(w4[0], w4[1], 0x7362), t3 = __byte_perm(w4[2], w4[3], 0x7362);
+		const uint32_t o4[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+		uint8_t *out = dst + ((size_t)(cd.map_offset + n0 + 4 * n4) * H + y) * WPS + x0 + 4 * xq;
+		const size_t map_stride = (size_t)H * WPS;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (4 * n4 + j < nb) *reinterpret_cast<uint32_t *>(out + (size_t)j * map_stride) = o4[j];
 	}
 }
 
