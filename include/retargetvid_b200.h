@@ -211,6 +211,11 @@ int rvb_crop_frames(rvb_ctx *ctx, const uint8_t *frames, int32_t n_frames, int32
 int rvb_format_boxes_txt(const int32_t *boxes, int64_t n_frames, char *out, int64_t cap, int64_t *len_out);
 int rvb_parse_boxes_txt(const char *text, int64_t len, int32_t *boxes, int64_t cap_frames, int64_t *n_frames_out);
 
+/* host-only: scipy.signal.butter(order, Wn) and lfilter_zi as the low-pass stage designs them (smartVidCrop.py:1601-1605):
+ * b, a: order + 1 doubles, zi: order doubles; *chunked_ok = 1 if the kernel evaluates this filter in parallel chunks, 0 if
+ * it is so ill conditioned that only scipy's sequential order of operations reproduces scipy's output */
+int rvb_debug_butter(int32_t order, double wn, double *b, double *a, double *zi, int32_t *chunked_ok);
+
 /* stage-level entry points used by the parity tests (device work only) */
 /* sc_clustering_filt on one uint8 map in host memory -- smartVidCrop.py:1062-1161 */
 int rvb_debug_cluster_labels(rvb_ctx *ctx, const rvb_params *p, const uint8_t *map_hw, int32_t h, int32_t w,

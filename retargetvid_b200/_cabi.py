@@ -31,7 +31,7 @@ RVB_MAPS_F32_NHW = 2
 EXPORTS = ['rvb_version', 'rvb_last_error', 'rvb_ctx_create', 'rvb_ctx_destroy', 'rvb_ctx_set_stream',
 		'rvb_ctx_synchronize', 'rvb_ctx_launch_count', 'rvb_ctx_last_map_kernel_ms', 'rvb_ctx_last_stage_ms', 'rvb_params_default',
 		'rvb_crop_track_batch', 'rvb_iou_batch_run', 'rvb_iou_mean_from_acc', 'rvb_debug_cluster_labels',
-		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms', 'rvb_ctx_last_host_us', 'rvb_format_boxes_txt', 'rvb_parse_boxes_txt']
+		'rvb_debug_smooth_series', 'rvb_ctx_phase_cycles', 'rvb_crop_frames', 'rvb_ctx_last_iou_kernel_ms', 'rvb_ctx_last_host_us', 'rvb_format_boxes_txt', 'rvb_parse_boxes_txt', 'rvb_debug_butter']
 
 
 class RvbError(RuntimeError):
@@ -114,9 +114,19 @@ def load_library():
 									C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
 	lib.rvb_ctx_last_host_us.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 	lib.rvb_format_boxes_txt.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+	lib.rvb_debug_butter.argtypes = [C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
 	lib.rvb_parse_boxes_txt.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
 	_lib = lib
 	return lib
+
+
+def debug_butter(order, wn):
+	"""(b, a, zi, chunked_ok) of the low-pass filter the library designs for scipy.signal.butter(order, wn)."""
+	lib = load_library()
+	b, a, zi = np.zeros(order + 1), np.zeros(order + 1), np.zeros(order)
+	ok = C.c_int32()
+	check(lib.rvb_debug_butter(order, float(wn), b.ctypes.data, a.ctypes.data, zi.ctypes.data, C.byref(ok)))
+	return b, a, zi, bool(ok.value)
 
 
 def format_boxes_txt(boxes):

@@ -110,6 +110,8 @@ struct rvb_ctx {
 	DevBuf phase;
 	bool chain_levels = true;   // cut-adjacent chains go through the split pipeline, one depth per set, on the side stream;
 	                            // RVB_CHAIN_MONO=1: the monolithic kernel walks them instead (the round-1 default)
+	struct CachedFilter { int order; double wn; FilterCoef fc; };
+	std::vector<CachedFilter> filter_cache;   // Butterworth designs by (order, Wn)
 	double host_us[6] = {0, 0, 0, 0, 0, 0};   // host time of the last crop_track call by section (rvb_ctx_last_host_us)
 	bool chain_levels_dense = false;   // RVB_CHAIN_LEVELS=1: also with the all-pairs Prim (slower: 3 more sets of 11 small launches)
 	int prim_variant[4] = {0, 0, 0, 0};
@@ -225,6 +227,70 @@ static void build_ring_table(RingTable &t) {
 	t.n_offsets = (int)offs.size();
 }
 
+// A Butterworth filter of high order and low cut-off is ill conditioned in transfer-function form: its output depends
+// on the ORDER of the floating-point operations at the 1e-7 .. 1e-3 level (order 7 at 1 Hz / 30 fps: 4e-4), and scipy's
+// own output carries that error.  lowpass_kernel evaluates filtfilt in 32 chunks per pass (filtfilt_warp); this probe
+// runs that evaluation and the sequential one on a test signal (two lengths, values in pixel range) and allows the chunked
+// form only where the two agree to 2e-9 -- there is a wide gap: order 5 at 2 Hz / 30 fps (the default) 4.5e-10, every
+// well-conditioned filter below that; order 5 at 1 Hz 1e-7, order 7 at 2 Hz 1.7e-7.
+static bool filtfilt_chunked_probe(const FilterCoef &fc) {
+	const int M = fc.order;
+	if (M < 1) return true;
+	auto step = [&](double *z, double x) -> double {
+		const double y = z[0] + fc.b[0] * x;
+		for (int i = 0; i < M - 1; ++i) z[i] = (z[i + 1] + x * fc.b[i + 1]) - y * fc.a[i + 1];
+		z[M - 1] = x * fc.b[M] - y * fc.a[M];
+		return y;
+	};
+	double worst = 0.0;
+	const int lengths[2] = {2700, 330};
+	for (int t = 0; t < 2; ++t) {
+		const int ne = lengths[t];
+		std::vector<double> x(ne), seq(ne), chk(ne);
+		for (int i = 0; i < ne; ++i) x[i] = 125.0 + 100.0 * sin(i / 27.5) + 10.0 * sin(i / 1.16) + ((i * 2654435761u >> 16) & 255) / 128.0;
+		seq = x; chk = x;
+		const int L = (ne + 31) >> 5;
+		double P[RVB_MAX_LP_ORDER][RVB_MAX_LP_ORDER];
+		for (int c = 0; c < M; ++c) {
+			double z[RVB_MAX_LP_ORDER] = {0};
+			z[c] = 1.0;
+			for (int n = 0; n < L; ++n) step(z, 0.0);
+			for (int r = 0; r < M; ++r) P[r][c] = z[r];
+		}
+		for (int pass = 0; pass < 2; ++pass) {
+			auto at = [&](int i) { return pass ? ne - 1 - i : i; };
+			// sequential
+			double z[RVB_MAX_LP_ORDER];
+			for (int i = 0; i < M; ++i) z[i] = fc.zi[i] * seq[at(0)];
+			for (int i = 0; i < ne; ++i) seq[at(i)] = step(z, seq[at(i)]);
+			// chunked
+			double E[32][RVB_MAX_LP_ORDER], S[32][RVB_MAX_LP_ORDER];
+			for (int k = 0; k < 32; ++k) {
+				double e[RVB_MAX_LP_ORDER] = {0};
+				for (int i = std::min(ne, k * L); i < std::min(ne, k * L + L); ++i) step(e, chk[at(i)]);
+				for (int r = 0; r < M; ++r) E[k][r] = e[r];
+			}
+			for (int r = 0; r < M; ++r) S[0][r] = fc.zi[r] * chk[at(0)];
+			for (int k = 1; k < 32; ++k)
+				for (int r = 0; r < M; ++r) {
+					double acc = E[k - 1][r];
+					for (int c = 0; c < M; ++c) acc += P[r][c] * S[k - 1][c];
+					S[k][r] = acc;
+				}
+			for (int k = 0; k < 32; ++k) {
+				double zz[RVB_MAX_LP_ORDER];
+				for (int r = 0; r < M; ++r) zz[r] = S[k][r];
+				for (int i = std::min(ne, k * L); i < std::min(ne, k * L + L); ++i) chk[at(i)] = step(zz, chk[at(i)]);
+			}
+		}
+		for (int i = 0; i < ne; ++i) {
+			const double d = fabs(seq[i] - chk[i]);
+			if (!(d <= worst)) worst = d;      // (NaN counts as a failure)
+		}
+	}
+	return worst <= 2e-9;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Butterworth low-pass design: scipy.signal.butter(order, Wn, 'lowpass') -> (b, a), and
 // scipy.signal.lfilter_zi(b, a) -- the calls made at smartVidCrop.py:1601-1605 (via filtfilt).
@@ -289,6 +355,7 @@ static void butter_design(int order, double wn, FilterCoef &fc) {
 		cs += fc.b[i] - fc.a[i] * fc.b[0];
 		fc.zi[i] = as * fc.zi[0] - cs;
 	}
+	fc.chunked_ok = filtfilt_chunked_probe(fc) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -797,8 +864,20 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 		int ci = -1;
 		for (size_t k = 0; k < coef_fr.size(); ++k) if (coef_fr[k] == cl.fr) ci = (int)k;
 		if (ci < 0) {
-			FilterCoef fc;
-			butter_design(p->lp_order, p->lp_cutoff / (0.5 * cl.fr), fc);
+			// (designs are kept per context: the conditioning probe inside butter_design costs ~0.2 ms)
+			const double wn = p->lp_cutoff / (0.5 * cl.fr);
+			const FilterCoef *hit = nullptr;
+			for (const auto &e : c->filter_cache)
+				if (e.order == p->lp_order && e.wn == wn) hit = &e.fc;
+			if (!hit) {
+				if (c->filter_cache.size() >= 64) c->filter_cache.clear();
+				rvb_ctx::CachedFilter e;
+				e.order = p->lp_order; e.wn = wn;
+				butter_design(p->lp_order, wn, e.fc);
+				c->filter_cache.push_back(e);
+				hit = &c->filter_cache.back().fc;
+			}
+			const FilterCoef fc = *hit;
 			coefs.push_back(fc);
 			coef_fr.push_back(cl.fr);
 			ci = (int)coefs.size() - 1;
@@ -1533,6 +1612,18 @@ extern "C" double rvb_iou_mean_from_acc(const uint64_t acc[2], int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // renderer crop
 // ---------------------------------------------------------------------------------------------
+// host-only: the filter the low-pass stage would run for (order, Wn)
+extern "C" int rvb_debug_butter(int32_t order, double wn, double *b, double *a, double *zi, int32_t *chunked_ok) {
+	if (!b || !a || !zi || !chunked_ok) return fail(RVB_ERR_INVALID, "NULL argument");
+	FilterCoef fc;
+	butter_design(order, wn, fc);
+	if (fc.order == 0) return fail(RVB_ERR_UNSUPPORTED, "order=%d Wn=%g: no filter (scipy raises; the reference falls back to moving averages)", order, wn);
+	for (int i = 0; i <= order; ++i) { b[i] = fc.b[i]; a[i] = fc.a[i]; }
+	for (int i = 0; i < order; ++i) zi[i] = fc.zi[i];
+	*chunked_ok = fc.chunked_ok;
+	return RVB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // a16: result text format (host)
 // ---------------------------------------------------------------------------------------------

@@ -30,6 +30,8 @@ struct FilterCoef {        // Butterworth low-pass in transfer-function form + l
 	double b[RVB_MAX_LP_ORDER + 1];
 	double a[RVB_MAX_LP_ORDER + 1];
 	double zi[RVB_MAX_LP_ORDER];
+	int chunked_ok;        // host probe (filtfilt_chunked_probe): the parallel-in-time evaluation stays within 2e-9 of the
+	                       // sequential one for this filter; otherwise the kernel runs the sequential recurrence
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -356,6 +358,55 @@ __global__ void interp_eval_kernel(const ShotDev *shots, const int *frame_shot, 
 // compile-time constant).
 struct FiltScratch { double P[8][8], E[32][8], S[32][8]; };
 
+// The sequential evaluation: scipy's lfilter loop operation for operation, on one lane.  Used when the filter is so ill
+// conditioned in transfer-function form (high order, low cut-off) that ANY other order of the same arithmetic moves the
+// result by more than the parity tolerance -- scipy's own output carries that error, so only its order reproduces it.
+template <int M>
+__device__ __forceinline__ void filtfilt_inplace(const FilterCoef &fc, double *buf, int ne) {
+	double b[M + 1], a[M + 1], zi[M], z[M];
+#pragma unroll
+	for (int i = 0; i <= M; ++i) { b[i] = fc.b[i]; a[i] = fc.a[i]; }
+#pragma unroll
+	for (int i = 0; i < M; ++i) zi[i] = fc.zi[i];
+	auto step = [&](double x) -> double {
+		const double y = __dadd_rn(z[0], __dmul_rn(b[0], x));
+#pragma unroll
+		for (int i = 0; i < M - 1; ++i) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(x, b[i + 1])), __dmul_rn(y, a[i + 1]));
+		z[M - 1] = __dsub_rn(__dmul_rn(x, b[M]), __dmul_rn(y, a[M]));
+		return y;
+	};
+	// (the next sample is loaded before the current one enters the serial chain)
+	const double e0 = buf[0];
+#pragma unroll
+	for (int i = 0; i < M; ++i) z[i] = zi[i] * e0;
+	double xn = e0;
+	for (int i = 0; i < ne; ++i) {
+		const double xc = xn;
+		if (i + 1 < ne) xn = buf[i + 1];
+		buf[i] = step(xc);
+	}
+	const double y0 = buf[ne - 1];
+#pragma unroll
+	for (int i = 0; i < M; ++i) z[i] = zi[i] * y0;
+	xn = y0;
+	for (int i = ne - 1; i >= 0; --i) {
+		const double xc = xn;
+		if (i > 0) xn = buf[i - 1];
+		buf[i] = step(xc);
+	}
+}
+
+template <int M>
+__device__ __forceinline__ void filtfilt_warp(const FilterCoef &fc, double *buf, int ne, int lane, struct FiltScratch &fs);
+
+template <int M>
+__device__ __forceinline__ void filtfilt_any(const FilterCoef &fc, double *buf, int ne, int lane, struct FiltScratch &fs) {
+	if (fc.chunked_ok) filtfilt_warp<M>(fc, buf, ne, lane, fs);
+	else if (lane == 0) filtfilt_inplace<M>(fc, buf, ne);
+}
+
+
+
 template <int M>
 __device__ __forceinline__ void filtfilt_warp(const FilterCoef &fc, double *buf, int ne, int lane, FiltScratch &fs) {
 	double b[M + 1], a[M + 1];
@@ -468,14 +519,14 @@ __global__ void __launch_bounds__(32) lowpass_kernel(const ShotDev *shots, int n
 		}
 		__syncwarp();
 		switch (m) {
-		case 1: filtfilt_warp<1>(fc, buf, ne, lane, lp_fs); break;
-		case 2: filtfilt_warp<2>(fc, buf, ne, lane, lp_fs); break;
-		case 3: filtfilt_warp<3>(fc, buf, ne, lane, lp_fs); break;
-		case 4: filtfilt_warp<4>(fc, buf, ne, lane, lp_fs); break;
-		case 5: filtfilt_warp<5>(fc, buf, ne, lane, lp_fs); break;
-		case 6: filtfilt_warp<6>(fc, buf, ne, lane, lp_fs); break;
-		case 7: filtfilt_warp<7>(fc, buf, ne, lane, lp_fs); break;
-		default: filtfilt_warp<8>(fc, buf, ne, lane, lp_fs); break;
+		case 1: filtfilt_any<1>(fc, buf, ne, lane, lp_fs); break;
+		case 2: filtfilt_any<2>(fc, buf, ne, lane, lp_fs); break;
+		case 3: filtfilt_any<3>(fc, buf, ne, lane, lp_fs); break;
+		case 4: filtfilt_any<4>(fc, buf, ne, lane, lp_fs); break;
+		case 5: filtfilt_any<5>(fc, buf, ne, lane, lp_fs); break;
+		case 6: filtfilt_any<6>(fc, buf, ne, lane, lp_fs); break;
+		case 7: filtfilt_any<7>(fc, buf, ne, lane, lp_fs); break;
+		default: filtfilt_any<8>(fc, buf, ne, lane, lp_fs); break;
 		}
 		__syncwarp();
 		for (int i = lane; i < cl; i += 32) { const double v = buf[edge + i]; out[i] = v; vmin = fmin(vmin, v); vmax = fmax(vmax, v); }

@@ -323,3 +323,27 @@ def test_result_text_format_and_parser_match_python():
 			[[int(c[0]), int(c[1]), int(c[2]), int(c[3])] for c in [ln.split(',') for ln in bad.splitlines()]]
 		with pytest.raises(_cabi.RvbError):
 			_cabi.parse_boxes_txt(bad)
+
+
+def test_butterworth_design_matches_scipy_and_conditioning_flag():
+	"""scipy.signal.butter + lfilter_zi as the library designs them on the host (smartVidCrop.py:1601-1605), and the probe
+	that decides whether filtfilt may run in parallel chunks: yes for every well-conditioned filter (the defaults of both
+	presets among them), no for high order at low cut-off, where only scipy's sequential order reproduces scipy."""
+	from scipy import signal
+	from retargetvid_b200 import _cabi
+	for order in (1, 2, 3, 4, 5, 6, 7, 8):
+		for cut, fr in ((2.0, 30.0), (1.0, 30.0), (2.0, 24.0), (3.5, 25.0), (5.0, 30.0)):
+			wn = cut / (0.5 * fr)
+			b, a, zi, ok = _cabi.debug_butter(order, wn)
+			rb, ra = signal.butter(order, wn, btype='low')
+			rzi = signal.lfilter_zi(rb, ra)
+			assert np.max(np.abs(b - rb) / np.abs(rb)) < 1e-13 and np.max(np.abs(a - ra) / np.abs(ra)) < 1e-13, (order, cut, fr)
+			if ok:
+				assert np.max(np.abs(zi - rzi) / np.abs(rzi)) < 1e-11, (order, cut, fr)
+	assert _cabi.debug_butter(5, 2.0 / 15.0)[3]            # ICIP-2021 defaults at 30 fps
+	assert _cabi.debug_butter(5, 2.0 / 12.0)[3]            # ... at 24 fps
+	assert _cabi.debug_butter(2, 1.0 / 15.0)[3]            # ISM-2021 preset (lp_order 2, lp_cutoff 1)
+	assert not _cabi.debug_butter(5, 1.0 / 15.0)[3]
+	assert not _cabi.debug_butter(7, 2.0 / 15.0)[3]
+	with pytest.raises(_cabi.RvbError):
+		_cabi.debug_butter(5, 1.5)                          # Wn >= 1: scipy raises, the reference falls back
