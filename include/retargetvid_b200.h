@@ -70,7 +70,9 @@ typedef struct rvb_params {
 	int32_t focus_stability;      /* smartVidCrop.py:2427-2473 */
 	int32_t min_d_jump;
 	int32_t skip;                 /* frames between saliency maps, used by the focus-stability duration */
-	int32_t np_int_compat;        /* 0: numpy >= 1.24 (np.int raises, diagonal jumps give 255), 1: numpy the reference pins */
+	int32_t np_int_compat;        /* the interpreter the reference runs on.  0: today's (numpy >= 1.24: np.int raises, so diagonal
+	                                 focus-stability jumps give 255; Python >= 3.12: the builtin sum() behind mean_cvrg_score is
+	                                 compensated); 1: the environment the reference pins (np.int exists; plain left-to-right sum) */
 	double  foces_stab_t;
 	double  foces_stab_s;
 	double  loess_w_secs;

@@ -1058,7 +1058,9 @@ __global__ void __launch_bounds__(NT, MapKernelCfg<NT, TPT, MODE>::kMinBlocks) m
 
 		// ---- resize_factor != 1: the clustering runs on a down-scaled copy (smartVidCrop.py:1078-1084);
 		// an all-zero map is returned untouched (:1064)
-		rz = a.resize_on && (S.tot != 0u);
+		// (with clust_filt off sc_clustering_filt is never called, smartVidCrop.py:2354-2366: no resize round trip; the
+		// centroid stage below still samples by the same factor)
+		rz = a.resize_on && a.clust_filt && (S.tot != 0u);
 		if (rz) {
 			uint8_t *small8 = smem + L.small;
 			for (int i = tid; i < (a.Hs * a.WSs) >> 2; i += NT) reinterpret_cast<uint32_t *>(small8)[i] = 0u;

@@ -1342,7 +1342,7 @@ extern "C" int rvb_crop_track_batch(rvb_ctx *c, const rvb_params *p, const rvb_b
 	boxes_kernel<<<(int)(((long long)NF * R + 255) / 256), 256, 0, st>>>(d_clips, d_fclip, NF, R, (const int *)(M + o_final),
 																		d_borders, H, W, d_dxs, d_dys, p->shift_time, d_boxes, d_dims);
 	double *d_cscore = (double *)(M + o_cscore), *d_mscore = (double *)(M + o_mscore);
-	clip_scores_kernel<<<(nc * 32 + 127) / 128, 128, 0, st>>>(d_clips, nc, d_mo, H, W, R, p->exit_on_low_cvrg, d_mscore, d_cscore);
+	clip_scores_kernel<<<(nc * 32 + 127) / 128, 128, 0, st>>>(d_clips, nc, d_mo, H, W, R, p->exit_on_low_cvrg, p->np_int_compat, d_mscore, d_cscore);
 	CU(cudaGetLastError());
 	c->launches += 7;
 

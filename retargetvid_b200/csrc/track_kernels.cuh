@@ -789,7 +789,7 @@ __global__ void boxes_kernel(const ClipDev *clips, const int *frame_clip, int n_
 // integers (any order); the coverage means are float64 sums in map order as the reference takes them
 // (smartVidCrop.py:1326-1329), kept sequential on one lane and only computed when the coverage score is on.
 __global__ void __launch_bounds__(128) clip_scores_kernel(const ClipDev *clips, int n_clips, const MapOut *mo, int H, int W, int n_ratios,
-														   int with_cvrg, double *map_scores, double *clip_scores) {
+														   int with_cvrg, int pinned_python, double *map_scores, double *clip_scores) {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (c >= n_clips) return;
@@ -805,11 +805,24 @@ __global__ void __launch_bounds__(128) clip_scores_kernel(const ClipDev *clips, 
 	if (lane == 0 && clip_scores) {
 		double *out = clip_scores + (size_t)c * (1 + n_ratios);
 		out[0] = (double)tot / ((double)H * (double)W * (double)cl.n_maps);
-		double cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		// sum(cvrg_scores) / len(cvrg_scores) (smartVidCrop.py:1329) as the interpreter computes it: the builtin sum() of
+		// Python >= 3.12 adds floats with Neumaier's compensated summation; the Python the reference pins (3.7) adds
+		// them left to right (pinned_python, set together with np_int_compat)
+		double cv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 		if (with_cvrg)
 			for (int i = 0; i < cl.n_maps; ++i)
-				for (int r = 0; r < n_ratios; ++r) cv[r] += mo[cl.map_offset + i].cvrg[r];
-		for (int r = 0; r < n_ratios; ++r) out[1 + r] = cv[r] / (double)cl.n_maps;
+				for (int r = 0; r < n_ratios; ++r) {
+					const double x = mo[cl.map_offset + i].cvrg[r];
+					const double t = __dadd_rn(cv[r], x);
+					if (!pinned_python)
+						cc[r] = __dadd_rn(cc[r], (fabs(cv[r]) >= fabs(x)) ? __dadd_rn(__dsub_rn(cv[r], t), x) : __dadd_rn(__dsub_rn(x, t), cv[r]));
+					cv[r] = t;
+				}
+		for (int r = 0; r < n_ratios; ++r) {
+			double sum = cv[r];
+			if (cc[r] != 0.0 && isfinite(cc[r])) sum = __dadd_rn(sum, cc[r]);
+			out[1 + r] = sum / (double)cl.n_maps;
+		}
 	}
 }
 
