@@ -39,8 +39,14 @@ def fixture_np_int(fx):
 	return bool(int(fx['np_int'])) if 'np_int' in fx else False
 
 
-def loess_tolerance(cl):
-	"""Stated tolerance (process pixels) between an accurate LOESS solve and the
-	reference's pinv of the uncentred normal equations, whose own error grows
-	with shot length (5e-12 @60, 2e-8 @300, 5e-5 @2000, 3.5e-2 @10000)."""
-	return max(1e-9, 4e-8 * (cl / 300.0) ** 4)
+def loess_tolerance(cl, window=None):
+	"""Stated tolerance (process pixels) between an accurate LOESS solve and the reference's pinv of the normal equations
+	in UNCENTRED x normalised over the whole shot (pyloess.py:16-24,61-95), whose own error grows with the ratio of shot
+	length to window: measured against a long-double solve 8e-9 @ (300, 59), 9e-8 @ (600, 59), 2e-7 @ (130, 11),
+	6e-7 @ (400, 35) (5e-12 @60, 2e-8 @300, 5e-5 @2000, 3.5e-2 @10000 at the default window).
+	window: the LOESS window in frames (default: the reference's at 30 fps, min(59, cl - 2) made odd)."""
+	if window is None:
+		window = min(59, cl - 2)
+		window -= (window % 2 == 0)
+	window = max(int(window), 3)
+	return max(1e-9, 4e-8 * ((cl / window) / (300.0 / 59.0)) ** 4)

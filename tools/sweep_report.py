@@ -18,15 +18,15 @@ only = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else None
 idx = only if only else list(range(n))
 cases = [t._random_case(i) for i in idx]
 with mp.get_context('fork').Pool(min(len(cases), os.cpu_count() or 1)) as pool:
-	wants = pool.map(t._oracle_one, [(vd, over, ratios, ex['cvrg_window'], ex['np_int']) for vd, over, ratios, ex in cases], chunksize=1)
+	wants = pool.map(t._oracle_or_error, [(vd, over, ratios, ex['cvrg_window'], ex['np_int']) for vd, over, ratios, ex in cases], chunksize=1)
 e = CropEngine(0)
 bad = 0
 for i, ((vd, over, ratios, ex), want) in zip(idx, zip(cases, wants)):
 	CP = svc.sc_init_crop_params()
 	CP.update(over)
 	res = e.run([vd], CP, ratios, detail=True, want_filtered=True, raise_on_clip_error=False, cvrg_window=ex['cvrg_window'], np_int=ex['np_int'])[0]
-	if res.status != 0:
-		print(i, 'status', res.status)
+	if res.status != 0 or isinstance(want, str):
+		print(i, 'status', res.status, 'oracle', want if isinstance(want, str) else 'ok')
 		continue
 	filt = np.transpose(res.filtered, (1, 2, 0))
 	dm = (filt != want[0]['filt']).any(axis=(0, 1))
