@@ -269,3 +269,43 @@ def test_random_parameter_sweep_vs_oracle(engine):
 	# before int() -- common when com_km=False makes the centres integers and focus stability freezes them)
 	assert flips <= sum(vd['fc'] for vd, _, _, _ in cases) // 50, flips
 	assert len(over_capacity) <= max(1, len(cases) // 16), over_capacity
+
+
+def test_random_batches_vs_oracle(engine):
+	"""4 calls of 6 random clips each -- mixed frame sizes (several process sizes in one call), lengths, cuts and map
+	kinds -- under one random parameter set per call: every clip equals the oracle run on that clip alone."""
+	from retargetvid_b200 import _cabi
+	from retargetvid_b200 import smartVidCrop as svc
+	meta, jobs = [], []
+	for b in range(4):
+		_, over, ratios, ex = _random_case(5000 + b)
+		clips = [_random_case(6000 + 8 * b + j)[0] for j in range(6)]
+		meta.append((over, ratios, ex, clips))
+		jobs += [(vd, over, ratios, ex['cvrg_window'], ex['np_int']) for vd in clips]
+	with mp.get_context('fork').Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+		wants = pool.map(_oracle_or_error, jobs, chunksize=1)
+	failures = []
+	k = 0
+	for b, (over, ratios, ex, clips) in enumerate(meta):
+		CP = svc.sc_init_crop_params()
+		CP.update(over)
+		rs = engine.run(clips, CP, ratios, detail=True, want_filtered=True, raise_on_clip_error=False,
+						cvrg_window=ex['cvrg_window'], np_int=ex['np_int'])
+		for j, (vd, res) in enumerate(zip(clips, rs)):
+			want = wants[k]
+			k += 1
+			if isinstance(want, str):
+				if res.status != _cabi.RVB_ERR_NO_CENTRES:
+					failures.append((b, j, 'the reference raises TypeError, status %d' % res.status))
+				continue
+			if res.status == _cabi.RVB_ERR_CAPACITY:
+				continue
+			tol_floor = 1e-8
+			if CP['lp_filt'] and not _cabi.debug_butter(int(CP['lp_order']), float(CP['lp_cutoff']) / (0.5 * float(vd['fr'])))[3]:
+				tol_floor = 2e-5
+			try:
+				assert res.status == 0
+				_check_clip(res, want, ratios, vd, 'batch %d clip %d' % (b, j), max(tol_floor, _loess_tol(vd, CP)))
+			except AssertionError as e:
+				failures.append((b, j, str(e)[:300], over))
+	assert not failures, failures
