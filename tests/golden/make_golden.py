@@ -154,6 +154,13 @@ CLIPS = {
 	# clustering on a 4x down-scaled copy taken with INTER_CUBIC (resize_type 2), dominant cluster by maximum
 	'resize_cubic': (dict(seed=2021, fc=130, shot_starts=[40, 90]),
 					dict(t_threshold=90, hdbscan_min=5, hdbscan_min_samples=3, resize_factor=4, resize_type=2), ['1:3', '4:5']),
+	# combinations the random sweep (tests/test_gpu_at_size.py) singled out: clustering off with a resize factor set (the
+	# reference then never enters sc_clustering_filt, so no down-/up-scaling round trip; only the centroid samples by the
+	# factor), and integer (argmax) centres frozen by focus stability under Savitzky-Golay smoothing
+	'noclust_resize': (dict(seed=2022, fc=140, shot_starts=[45, 100]),
+					dict(clust_filt=False, resize_factor=4, resize_type=1, t_threshold=90), ['1:3', '4:5']),
+	'argmax_focus': (dict(seed=2023, fc=160, shot_starts=[70]),
+					dict(com_km=False, focus_stability=True, foces_stab_t=60, foces_stab_s=1.0, min_d_jump=5, loess_filt=0, lp_order=3, lp_cutoff=2.0), ['1:3', '3:1']),
 	# a different sampling table: every 3rd frame gets a map, 24 fps
 	'skip3_fr24': (dict(seed=2016, fc=150, fr=24.0, skip=3, shot_starts=[75]), {}, ['9:16']),
 }

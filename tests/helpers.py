@@ -8,7 +8,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 CLIP_NAMES = ['c1_default', 'multishot', 'fr25', 'hd1080', 'constant', 'noise', 'few_points',
 			'sumsel_min5', 'noclose_nolp', 'savgol_argmax', 'border', 'empties', 'best_settings', 'best_hd_fr25',
-			'shift_deg1', 'resize_nearest', 'skip3_fr24', 'best_npint', 'border_hd_multishot', 'loess_w3_bias', 'resize_area2', 'resize_cubic']
+			'shift_deg1', 'resize_nearest', 'skip3_fr24', 'best_npint', 'border_hd_multishot', 'loess_w3_bias', 'resize_area2', 'resize_cubic', 'noclust_resize', 'argmax_focus']
 
 ORACLE_ONLY_NAMES = []   # every reference fixture is also run through the CUDA path
 
