@@ -270,18 +270,28 @@ def make_hdbscan_fixture():
 	warnings.filterwarnings('ignore')
 	out = {}
 	idx = 0
-	for seed, kind, mcs, ms, thr in ((11, 'blobs', 26, None, 120), (12, 'blobs', 26, None, 120),
-									(13, 'blobs', 5, 3, 90), (14, 'noise', 26, None, 120),
-									(15, 'noise', 5, 3, 120), (16, 'blobs', 10, None, 150)):
+	# (the first six rows are the round-1 fixture; the rest covers the (min_cluster_size, min_samples) combinations the
+	# random parameter sweep draws, on every kind of map, 2 maps each)
+	configs = [(11, 'blobs', 26, None, 120, 2), (12, 'blobs', 26, None, 120, 2), (13, 'blobs', 5, 3, 90, 2),
+			(14, 'noise', 26, None, 120, 2), (15, 'noise', 5, 3, 120, 2), (16, 'blobs', 10, None, 150, 2)]
+	seed = 100
+	for mcs in (5, 12, 26, 40, 80):
+		for ms in (None, 3, 8, 15):
+			for kind, thr in (('blobs', 90), ('noise', 120), ('few_points', 60), ('blobs', 150)):
+				configs.append((seed, kind, mcs, ms, thr, 5))
+				seed += 1
+	for seed, kind, mcs, ms, thr, step in configs:
 		vd = synth.make_clip(seed, fc=40, shot_starts=[20], kind=kind)
 		maps = np.transpose(vd['smaps'], (2, 0, 1))
-		for i in range(0, maps.shape[0], 2):
+		for i in range(0, maps.shape[0], step):
 			m = maps[i].copy()
 			m[m < thr] = 0
 			ys, xs = np.nonzero(m)
 			if len(ys) <= mcs + 1:
 				continue
 			P = np.stack([ys, xs], 1)
+			if (ms or mcs) + 1 > len(P):
+				continue      # (the library raises: min_samples must be at most the number of points)
 			lab = ref_harness._SklearnHDBSCANStandIn(min_cluster_size=mcs, min_samples=ms, metric='sqeuclidean',
 													cluster_selection_method='eom', allow_single_cluster=True).fit_predict(P)
 			out['P_%d' % idx] = P.astype(np.int16)
