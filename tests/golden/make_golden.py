@@ -259,6 +259,15 @@ def make_loess_fixture():
 		out['y_%d' % cl] = y
 		out['w_%d' % cl] = np.array(w)
 		out['est_%d' % cl] = np.array([lo.estimate(j, window=w, use_matrix=False, degree=2) for j in range(cl)])
+	# narrow and wide windows, both degrees (what other frame rates / loess_w_secs / loess_degree give): key suffix cl_w_deg
+	extra = ((67, 11, 2), (130, 11, 2), (150, 23, 1), (400, 35, 2), (600, 179, 2), (200, 119, 1), (90, 87, 2))
+	for cl, w, deg in extra:
+		t = np.array(list(range(cl)))
+		y = 120 + 40 * np.sin(t / 37.0) + 15 * np.sin(t / 5.0) + rng.normal(0, 2.0, cl)
+		lo = pyloess.Loess(t, y)
+		out['y_%d_%d_%d' % (cl, w, deg)] = y
+		out['est_%d_%d_%d' % (cl, w, deg)] = np.array([lo.estimate(j, window=w, use_matrix=False, degree=deg) for j in range(cl)])
+	out['extra'] = np.array(extra)
 	np.savez_compressed(os.path.join(HERE, 'loess_fixture.npz'), **out)
 	print('loess fixture written')
 

@@ -166,6 +166,11 @@ def test_oracle_pyloess_and_eval_golden():
 		# the reference's pinv of the uncentred normal equations is itself only reproducible to this level
 		# across BLAS/SIMD code paths (the fixture was generated with numpy's SIMD dispatch off)
 		assert np.max(np.abs(np.array(got) - z['est_%d' % cl])) <= loess_tolerance(cl)
+	# narrow / wide windows and degree 1: the tolerance follows (shot length / window)^4
+	for cl, w, deg in z['extra']:
+		key = '%d_%d_%d' % (cl, w, deg)
+		got = sc_oracle.loess_handler(np.arange(cl), z['y_' + key], 1, int(w), int(deg))
+		assert np.max(np.abs(np.array(got) - z['est_' + key])) <= loess_tolerance(int(cl), int(w)), key
 	# evaluator golden on the first 25 videos, 1-3, annotator 1
 	e = np.load(os.path.join(GOLDEN, 'eval_fixture.npz'))
 	lens = e['annot_len_1_1-3']

@@ -188,6 +188,16 @@ def test_smooth_series_vs_pyloess_fixture(engine):
 		lp, sm = engine.ctx.debug_smooth_series(p, y, fr)
 		assert np.array_equal(lp, y)
 		assert np.max(np.abs(sm - want)) <= loess_tolerance(cl), (cl, np.max(np.abs(sm - want)))
+	# narrow / wide windows and degree 1 (other frame rates, loess_w_secs, loess_degree)
+	for cl, w, deg in z['extra']:
+		key = '%d_%d_%d' % (cl, w, deg)
+		p = _cabi.rvb_params()
+		engine.ctx.lib.rvb_params_default(p, 0)
+		p.lp_filt = 0
+		p.loess_w_secs = 1.0
+		p.loess_degree = int(deg)
+		lp, sm = engine.ctx.debug_smooth_series(p, z['y_' + key], float(w))
+		assert np.max(np.abs(sm - z['est_' + key])) <= loess_tolerance(int(cl), int(w)), (key, np.max(np.abs(sm - z['est_' + key])))
 
 
 def test_batch_equals_single(engine):
