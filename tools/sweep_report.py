@@ -1,5 +1,5 @@
 """Runs the random-parameter sweep of tests/test_gpu_at_size.py case by case and prints one line per failing case
-(stage that differs first, parameters): python tools/sweep_report.py [n_cases] [case,case,...|-] [batches]
+(stage that differs first, parameters): python tools/sweep_report.py [n_cases] [case,case,...|first:last|-] [batches]
 (`batches`: also 10 calls of 8 random clips each -- mixed frame sizes, lengths and cuts -- under one random parameter set)"""
 import multiprocessing as mp
 import os
@@ -15,7 +15,13 @@ from retargetvid_b200 import _cabi, smartVidCrop as svc  # noqa: E402
 from retargetvid_b200.engine import CropEngine  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-only = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 and sys.argv[2] not in ('', '-') else None
+only = None
+if len(sys.argv) > 2 and sys.argv[2] not in ('', '-'):
+	if ':' in sys.argv[2]:
+		a, b = sys.argv[2].split(':')
+		only = list(range(int(a), int(b)))
+	else:
+		only = [int(v) for v in sys.argv[2].split(',')]
 idx = only if only else list(range(n))
 cases = [t._random_case(i) for i in idx]
 with mp.get_context('fork').Pool(max(1, min(len(cases), os.cpu_count() or 1))) as pool:
@@ -39,7 +45,7 @@ for i, ((vd, over, ratios, ex), want) in zip(idx, zip(cases, wants)):
 	if dm.any() or ddx > 1e-9 or dxs > 1e-6 or any(db):
 		bad += 1
 		npts = [int((want[0]['filt'][:, :, m] > 0).sum()) for m in np.nonzero(dm)[0][:4]]
-		if only:
+		if only and len(only) <= 16:
 			print('  ratios', ratios, 'cvrg got', [float(v) for v in res.cvrg_scores], 'want', [w['cvrg'] for w in want], 'dims', [list(d) for d in res.dims])
 			for k in range(len(ratios)):
 				df = np.nonzero((res.boxes[k] != want[k]['bbs']).any(axis=1))[0]
